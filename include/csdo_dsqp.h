@@ -1,0 +1,197 @@
+/*
+ * csdo_dsqp.h -- C ABI of the B200-native DSQP refine stage.
+ *
+ * This is the drop-in boundary for ONE path of YangSVM/CSDOTrajectoryPlanning:
+ * the decentralized-SQP refine stage that the reference runs inside the
+ * constructor of `SolverDSQP` (reference sqp/dsqp_solver.h:24-47,
+ * sqp/dsqp_solver.cc:1133-1248), plus the two pre-process functions that feed
+ * it (reference sqp/inter_agent_cons.cc:12-140) and the corridor builder it
+ * calls (reference sqp/corridor.cc:124-248).
+ *
+ * The reference has no C ABI (it is one C++ executable); these entry points
+ * are what a cgo/ctypes/C++ binding for that path binds.  The C++ shim that
+ * keeps the reference's own class interface lives in include/csdo/dsqp_solver.h.
+ *
+ * Conventions: plain pointers and sizes, caller owns every buffer, int return
+ * codes (0 = ok), no exceptions cross the boundary, one CUDA stream per
+ * handle, a handle is not thread-safe.  There is NO CPU fallback: every
+ * compute entry point fails with CSDO_ERR_CUDA when no sm_100 device is
+ * usable.
+ *
+ * Batch layout (all FP64 unless noted).  A batch is n_inst independent
+ * instances; agents are numbered globally, instance i owns agents
+ * [inst_agent_ptr[i], inst_agent_ptr[i+1]).  All agents of an instance share
+ * the horizon inst_nt[i] (reference inter_agent_cons.cc:320-345 pads to the
+ * longest path).  Agent a stores its horizon at time-step offset
+ * agent_off[a] (agent_off[a+1]-agent_off[a] == Nt of its instance):
+ *   guess / traj : 6 planes of Nt doubles at 6*agent_off[a]:
+ *                  x[Nt] y[Nt] yaw[Nt] steer[Nt] v[Nt] w[Nt]
+ *                  (v,w: Nt-1 valid, last entry ignored on input, 0 on output;
+ *                  the field names follow OptimizeResult, sqp/common.h:14-22,
+ *                  with w == d_steer)
+ *   corridors    : 8 planes of Nt doubles at 8*agent_off[a], in the field
+ *                  order of `Corridor` (sqp/corridor.h:8-11):
+ *                  xf_min xf_max yf_min yf_max xr_min xr_max yr_min yr_max
+ * Planes: CSR over agents, plane_ptr[n_agents+1]; plane k has time plane_t[k]
+ * and 12 doubles in the member order of `InterPlane`
+ * (sqp/inter_agent_cons.h:47-53): a,b,c of f2f, f2r, r2f, r2r.  Within an
+ * agent planes are sorted by t (the reference's push order,
+ * inter_agent_cons.cc:26-31,136-137).
+ * Obstacles: CSR over instances, 3 doubles (x, y, r) each, in the iteration
+ * order of the caller's container (reference: std::unordered_set<Location>).
+ */
+#ifndef CSDO_DSQP_H_
+#define CSDO_DSQP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CSDO_OK 0
+#define CSDO_ERR_INVALID 1     /* bad argument / inconsistent batch */
+#define CSDO_ERR_CUDA 2        /* no usable device or a CUDA call failed */
+#define CSDO_ERR_UNSUPPORTED 3 /* horizon too long for the kernel's layout */
+#define CSDO_ERR_NOMEM 4
+
+/* OSQP status codes that can leave the QP step (osqp/constants.h of 0.6.x). */
+#define CSDO_QP_SOLVED 1
+#define CSDO_QP_SOLVED_INACCURATE 2
+#define CSDO_QP_PRIMAL_INFEASIBLE_INACCURATE 3
+#define CSDO_QP_MAX_ITER_REACHED (-2)
+#define CSDO_QP_PRIMAL_INFEASIBLE (-3)
+#define CSDO_QP_NON_CVX (-7)
+#define CSDO_QP_UNSOLVED (-10)
+
+/*
+ * Parameters.  Vehicle constants follow `Constants` (common/motion_planning.h
+ * :9-67, values from config.yaml via common/motion_planning.cc:54-109), the
+ * SQP block follows `QpParm` (sqp/common.h:39-52, sqp/utils.cc:34-59), the OSQP
+ * block holds what osqp_set_default_settings() of OSQP 0.6.x leaves in force
+ * at sqp/dsqp_solver.cc:480-487.
+ */
+typedef struct csdo_params {
+  /* vehicle */
+  double f2x;       /* front disc offset,  (3 LF - LB)/4 */
+  double r2x;       /* rear disc offset,   (LF - 3 LB)/4 */
+  double rv;        /* disc radius */
+  double WB;        /* wheel base */
+  double steer_max; /* atan(WB / r), dsqp_solver.cc:1178 */
+  double LF, LB, car_width; /* rectangle, used by the SAT legality flag only */
+  /* QpParm */
+  double r_trust;
+  double max_omega;
+  double max_v;
+  double delta_solution_threshold;
+  double dt;
+  int32_t max_iter;       /* SQP iterations (config max_iter) */
+  int32_t osqp_max_iter;  /* ADMM iterations per QP */
+  int32_t fixed_corridor; /* bool */
+  /* OSQP 0.6.x settings */
+  int32_t adaptive_rho_interval; /* PINNED (reference: wall-clock dependent); 25 */
+  int32_t scaling;               /* Ruiz passes, 10 */
+  int32_t check_termination;     /* 25 */
+  int32_t adaptive_rho;          /* 1 */
+  double rho, sigma, alpha;
+  double eps_abs, eps_rel, eps_prim_inf, eps_dual_inf;
+  double adaptive_rho_tolerance;
+  /* corridor growth (sqp/corridor.h:72 defaults) */
+  double box_ds;    /* 0.1 */
+  double box_limit; /* 10.0 */
+} csdo_params;
+
+typedef struct csdo_batch {
+  int32_t n_inst;
+  int32_t n_agents;
+  const int32_t *inst_agent_ptr; /* [n_inst+1] */
+  const int32_t *inst_nt;        /* [n_inst] */
+  const double *inst_dims;       /* [n_inst][2] dimx, dimy */
+  const int32_t *obs_ptr;        /* [n_inst+1] */
+  const double *obs;             /* [sum No][3] */
+  const int64_t *agent_off;      /* [n_agents+1], time-step offsets */
+  const double *guess;           /* [6 * agent_off[n_agents]] */
+  const int32_t *plane_ptr;      /* [n_agents+1] */
+  const int32_t *plane_t;        /* [sum K] */
+  const double *plane_abc;       /* [sum K][12] */
+} csdo_batch;
+
+typedef struct csdo_result {
+  double *traj;               /* [6 * total steps] */
+  double *corridors;          /* [8 * total steps] */
+  int32_t *status;            /* [n_agents] OSQP code of the agent's LAST QP */
+  int32_t *sqp_iters;         /* [n_agents] == SolverDSQP::num_iterations */
+  int32_t *n_qp;              /* [n_agents] QPs solved (== sqp_iters) */
+  int32_t *admm_iters;        /* [n_agents] ADMM iterations summed over QPs */
+  int32_t *n_factor;          /* [n_agents] KKT factorizations summed over QPs */
+  double *objective;          /* [n_agents] objective of the last QP at its output */
+  int32_t *inst_status;       /* [n_inst] == SolverDSQP::getSolverStatus() */
+  int32_t *inst_static_legal; /* [n_inst] == get_initial_static_legal() */
+} csdo_result;
+
+typedef struct csdo_handle csdo_handle;
+
+/* Fills the values the reference computes from its shipped config.yaml. */
+void csdo_default_params(csdo_params *p);
+
+/* Library / build identification ("csdo-dsqp-b200 <ver> sm_100a"). */
+const char *csdo_version(void);
+
+/* Create a solver bound to CUDA device `device`.  Replaces nothing in the
+ * reference (it has no device); owns the stream, scratch and work queue. */
+int csdo_create(const csdo_params *params, int device, csdo_handle **out);
+void csdo_destroy(csdo_handle *h);
+const char *csdo_last_error(const csdo_handle *h);
+
+/*
+ * Refine a batch: for every instance what `SolverDSQP::SolverDSQP` does
+ * (dsqp_solver.cc:1133-1248): initial corridors, per-agent SQP loop with an
+ * OSQP-style ADMM per QP, corridor regeneration, feasibility early exit,
+ * status aggregation.  HOST pointers; copies in, runs, copies out, blocks.
+ */
+int csdo_refine(csdo_handle *h, const csdo_batch *in, csdo_result *out);
+
+/* Same, DEVICE pointers in both structs; enqueued on `cuda_stream` (a
+ * cudaStream_t, 0 = the handle's stream); returns without synchronizing. */
+int csdo_refine_device(csdo_handle *h, const csdo_batch *in, csdo_result *out,
+                       void *cuda_stream);
+
+/* Kernel-launch and timing facts of the last refine on this handle
+ * (launches: kernels enqueued; smem_bytes/block/grid: the DSQP kernel's
+ * configuration; tier: 0 all-shared, 1 read-only rows in global, 2 band
+ * factor in global). */
+typedef struct csdo_launch_info {
+  int32_t launches;
+  int32_t grid, block, smem_bytes, tier, ctas_per_sm;
+} csdo_launch_info;
+int csdo_last_launch(const csdo_handle *h, csdo_launch_info *info);
+
+/*
+ * Initial corridors only (reference calcCorridors, sqp/corridor.cc:164-248,
+ * or, with double_centres != 0, the regeneration of
+ * SolverDSQP::updateCorridor, dsqp_solver.cc:818-872).  Uses in->guess x,y,yaw.
+ * HOST pointers.  corridors: [8*steps]; box_status: [2*steps][2] int32
+ * (success, initial_status) front then rear per step, may be NULL.
+ */
+int csdo_corridors(csdo_handle *h, const csdo_batch *in, int double_centres,
+                   double *corridors, int32_t *box_status,
+                   int32_t *inst_static_legal);
+
+/*
+ * Pre-process: neighbour pairs + separating planes
+ * (findNeighborPairsByTrustRegion, inter_agent_cons.cc:12-49 and
+ * calcEqualInterPlanes, :71-140).  Two calls: count fills plane_ptr
+ * [n_agents+1] and inst_inter_legal[n_inst] (the function's return value);
+ * the caller then allocates plane_t / plane_abc for plane_ptr[n_agents]
+ * planes and calls fill.  HOST pointers; in->plane_* are ignored.
+ */
+int csdo_planes_count(csdo_handle *h, const csdo_batch *in, int32_t *plane_ptr,
+                      int32_t *inst_inter_legal);
+int csdo_planes_fill(csdo_handle *h, const csdo_batch *in,
+                     const int32_t *plane_ptr, int32_t *plane_t,
+                     double *plane_abc);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSDO_DSQP_H_ */
