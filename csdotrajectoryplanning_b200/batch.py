@@ -21,6 +21,7 @@ class CsdoBatch(C.Structure):
         ("inst_dims", C.c_void_p), ("obs_ptr", C.c_void_p), ("obs", C.c_void_p),
         ("agent_off", C.c_void_p), ("guess", C.c_void_p),
         ("plane_ptr", C.c_void_p), ("plane_t", C.c_void_p), ("plane_abc", C.c_void_p),
+        ("agent_order", C.c_void_p),
     ]
 
 
@@ -121,6 +122,7 @@ class Batch:
             arr = getattr(self, name)
             assert arr.flags["C_CONTIGUOUS"]
             setattr(b, name, arr.ctypes.data if arr.size else None)
+        b.agent_order = None
         return b
 
     def select_instances(self, idx: Sequence[int]) -> "Batch":

@@ -1,0 +1,375 @@
+// C ABI of the DSQP refine path (include/csdo_dsqp.h): handle, device memory,
+// host<->device staging, launch configuration.  No CPU fallback: without a
+// usable sm_100 device every compute entry point returns CSDO_ERR_CUDA.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "csdo_dsqp.h"
+#include "dsqp_launch.h"
+
+using namespace csdo;
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+};
+
+struct csdo_handle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  csdo_params P{};
+  std::string err;
+  int num_sms = 0, smem_limit = 0;
+  DevBuf scratch, queue, step_cnt;
+  std::vector<DevBuf> stage;  // staging buffers of the host-pointer entry points
+  csdo_launch_info last{};
+};
+
+namespace {
+
+bool set_err(csdo_handle *h, const char *what, cudaError_t e) {
+  if (e == cudaSuccess) return false;
+  if (h) h->err = std::string(what) + ": " + cudaGetErrorString(e);
+  return true;
+}
+
+int ensure(csdo_handle *h, DevBuf &b, size_t bytes) {
+  if (bytes <= b.cap) return CSDO_OK;
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr; b.cap = 0;
+  size_t want = bytes + bytes / 8 + 256;
+  if (set_err(h, "cudaMalloc", cudaMalloc(&b.p, want))) return CSDO_ERR_NOMEM;
+  b.cap = want;
+  return CSDO_OK;
+}
+
+struct Meta {
+  int max_nt = 0, max_k = 0;
+  int64_t steps = 0;
+  int n_obs = 0, n_planes = 0;
+};
+
+int validate_host(csdo_handle *h, const csdo_batch *in, bool need_planes, Meta &m) {
+  if (!in || in->n_inst < 0 || in->n_agents < 0) { h->err = "null or negative-sized batch"; return CSDO_ERR_INVALID; }
+  if (in->n_agents == 0) return CSDO_OK;
+  if (!in->inst_agent_ptr || !in->inst_nt || !in->inst_dims || !in->obs_ptr || !in->agent_off || !in->guess ||
+      (need_planes && !in->plane_ptr)) { h->err = "null array in batch"; return CSDO_ERR_INVALID; }
+  if (in->inst_agent_ptr[0] != 0 || in->inst_agent_ptr[in->n_inst] != in->n_agents) {
+    h->err = "inst_agent_ptr does not cover the agents"; return CSDO_ERR_INVALID;
+  }
+  for (int i = 0; i < in->n_inst; ++i) {
+    const int nt = in->inst_nt[i];
+    if (nt < 3) { h->err = "horizon < 3"; return CSDO_ERR_INVALID; }
+    if (nt > kMaxThreads) { h->err = "horizon exceeds 512 steps"; return CSDO_ERR_UNSUPPORTED; }
+    m.max_nt = std::max(m.max_nt, nt);
+    for (int a = in->inst_agent_ptr[i]; a < in->inst_agent_ptr[i + 1]; ++a)
+      if (in->agent_off[a + 1] - in->agent_off[a] != nt) { h->err = "agent_off inconsistent with inst_nt"; return CSDO_ERR_INVALID; }
+  }
+  m.steps = in->agent_off[in->n_agents];
+  m.n_obs = in->obs_ptr[in->n_inst];
+  if (need_planes) {
+    for (int a = 0; a < in->n_agents; ++a) m.max_k = std::max(m.max_k, in->plane_ptr[a + 1] - in->plane_ptr[a]);
+    m.n_planes = in->plane_ptr[in->n_agents];
+    if (m.n_planes > 0 && (!in->plane_t || !in->plane_abc)) { h->err = "null plane arrays"; return CSDO_ERR_INVALID; }
+  }
+  return CSDO_OK;
+}
+
+// upload one host array into staging slot `slot`
+template <class T>
+int upload(csdo_handle *h, int slot, const T *src, size_t n, const T **dst) {
+  if ((int)h->stage.size() <= slot) h->stage.resize(slot + 1);
+  int rc = ensure(h, h->stage[slot], std::max<size_t>(n * sizeof(T), 16));
+  if (rc) return rc;
+  if (n && set_err(h, "cudaMemcpyAsync H2D",
+                   cudaMemcpyAsync(h->stage[slot].p, src, n * sizeof(T), cudaMemcpyHostToDevice, h->stream)))
+    return CSDO_ERR_CUDA;
+  *dst = static_cast<const T *>(h->stage[slot].p);
+  return CSDO_OK;
+}
+template <class T>
+int devalloc(csdo_handle *h, int slot, size_t n, T **dst) {
+  if ((int)h->stage.size() <= slot) h->stage.resize(slot + 1);
+  int rc = ensure(h, h->stage[slot], std::max<size_t>(n * sizeof(T), 16));
+  if (rc) return rc;
+  *dst = static_cast<T *>(h->stage[slot].p);
+  return CSDO_OK;
+}
+template <class T>
+int download(csdo_handle *h, T *dst, const T *src, size_t n) {
+  if (!dst || !n) return CSDO_OK;
+  if (set_err(h, "cudaMemcpyAsync D2H", cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, h->stream)))
+    return CSDO_ERR_CUDA;
+  return CSDO_OK;
+}
+
+int upload_batch(csdo_handle *h, const csdo_batch *in, const Meta &m, bool planes, DevBatch &B) {
+  int rc;
+  B.n_inst = in->n_inst; B.n_agents = in->n_agents;
+  if ((rc = upload(h, 0, in->inst_agent_ptr, (size_t)in->n_inst + 1, &B.inst_agent_ptr))) return rc;
+  if ((rc = upload(h, 1, in->inst_nt, (size_t)in->n_inst, &B.inst_nt))) return rc;
+  if ((rc = upload(h, 2, in->inst_dims, (size_t)2 * in->n_inst, &B.inst_dims))) return rc;
+  if ((rc = upload(h, 3, in->obs_ptr, (size_t)in->n_inst + 1, &B.obs_ptr))) return rc;
+  if ((rc = upload(h, 4, in->obs, (size_t)3 * m.n_obs, &B.obs))) return rc;
+  if ((rc = upload(h, 5, in->agent_off, (size_t)in->n_agents + 1, &B.agent_off))) return rc;
+  if ((rc = upload(h, 6, in->guess, (size_t)6 * m.steps, &B.guess))) return rc;
+  B.plane_ptr = nullptr; B.plane_t = nullptr; B.plane_abc = nullptr; B.agent_order = nullptr;
+  if (planes) {
+    if ((rc = upload(h, 7, in->plane_ptr, (size_t)in->n_agents + 1, &B.plane_ptr))) return rc;
+    if ((rc = upload(h, 8, in->plane_t, (size_t)m.n_planes, &B.plane_t))) return rc;
+    if ((rc = upload(h, 9, in->plane_abc, (size_t)12 * m.n_planes, &B.plane_abc))) return rc;
+  }
+  return CSDO_OK;
+}
+
+DevBatch as_dev(const csdo_batch *in) {
+  DevBatch B;
+  B.n_inst = in->n_inst; B.n_agents = in->n_agents;
+  B.inst_agent_ptr = in->inst_agent_ptr; B.inst_nt = in->inst_nt; B.inst_dims = in->inst_dims;
+  B.obs_ptr = in->obs_ptr; B.obs = in->obs; B.agent_off = in->agent_off; B.guess = in->guess;
+  B.plane_ptr = in->plane_ptr; B.plane_t = in->plane_t; B.plane_abc = in->plane_abc;
+  B.agent_order = in->agent_order;
+  return B;
+}
+
+// configure + enqueue the refine kernels on device-resident data
+int run_refine(csdo_handle *h, const DevBatch &B, const DevOut &O, int max_nt, int max_k, cudaStream_t stream) {
+  if (B.n_agents == 0) return CSDO_OK;
+  if (max_nt < 3) { h->err = "horizon < 3"; return CSDO_ERR_INVALID; }
+  if (max_nt > kMaxThreads) { h->err = "horizon exceeds 512 steps"; return CSDO_ERR_UNSUPPORTED; }
+  const int NT = (max_nt + 31) & ~31;
+  const int KMAX = std::max(4, (max_k + 3) & ~3);
+  int ctas_smem = 0;
+  Layout LY = make_layout(NT, KMAX, h->smem_limit, &ctas_smem);
+  if (LY.NT == 0) { h->err = "horizon does not fit the shared-memory layout"; return CSDO_ERR_UNSUPPORTED; }
+  const int block = std::max(64, NT);
+  int occ = refine_occupancy(block, LY.smem_doubles * 8);
+  if (occ < 1) { h->err = "kernel cannot be resident (registers/shared memory)"; return CSDO_ERR_CUDA; }
+  const int grid = std::min(B.n_agents, h->num_sms * occ);
+  int rc;
+  if ((rc = ensure(h, h->scratch, (size_t)grid * LY.slot_doubles * sizeof(double)))) return rc;
+  if ((rc = ensure(h, h->queue, 64))) return rc;
+  if (set_err(h, "launch_refine",
+              launch_refine(B, O, h->P, LY, static_cast<double *>(h->scratch.p), static_cast<int *>(h->queue.p),
+                            grid, block, stream)))
+    return CSDO_ERR_CUDA;
+  h->last.launches = 3;
+  h->last.grid = grid; h->last.block = block; h->last.smem_bytes = LY.smem_doubles * 8;
+  h->last.tier = LY.tier; h->last.ctas_per_sm = occ;
+  return CSDO_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void csdo_default_params(csdo_params *p) {
+  // common/motion_planning.cc:54-109 on the shipped config.yaml; Constants are float
+  const float r = 3.0f, deltat = 0.706f, LF = 2.0f, LB = 1.0f, carWidth = 2.0f, WB = 1.0f;
+  std::memset(p, 0, sizeof(*p));
+  p->f2x = (float)(1 / 4.0 * (3.0 * LF - LB));
+  p->r2x = (float)(1 / 4.0 * (LF - 3.0 * LB));
+  p->rv = (float)(1.0 / 2.0 * pow(pow(LF + LB, 2) / 4 + carWidth * carWidth, 0.5));
+  p->WB = WB;
+  p->steer_max = atan((double)WB / r);  // dsqp_solver.cc:1178
+  p->LF = LF; p->LB = LB; p->car_width = carWidth;
+  // sqp/utils.cc:34-59
+  p->r_trust = 2.0; p->max_omega = 0.07; p->max_v = 1.0; p->delta_solution_threshold = 1.0;
+  const int num_interpolation = 2;
+  const double decelerate_factor = 0.8;
+  p->dt = r * deltat / p->max_v / (num_interpolation + 1) / decelerate_factor;
+  p->max_iter = 10; p->osqp_max_iter = 400; p->fixed_corridor = 0;
+  // osqp_set_default_settings (OSQP 0.6.x) + the pinned rho interval
+  p->adaptive_rho_interval = 25; p->scaling = 10; p->check_termination = 25; p->adaptive_rho = 1;
+  p->rho = 0.1; p->sigma = 1e-6; p->alpha = 1.6;
+  p->eps_abs = 1e-3; p->eps_rel = 1e-3; p->eps_prim_inf = 1e-4; p->eps_dual_inf = 1e-4;
+  p->adaptive_rho_tolerance = 5.0;
+  p->box_ds = 0.1; p->box_limit = 10.0;
+}
+
+const char *csdo_version(void) { return "csdo-dsqp-b200 0.1 sm_100a"; }
+
+int csdo_create(const csdo_params *params, int device, csdo_handle **out) {
+  if (!out) return CSDO_ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return CSDO_ERR_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return CSDO_ERR_CUDA;
+  if (prop.major != 10) return CSDO_ERR_CUDA;  // sm_100a code only
+  if (cudaSetDevice(device) != cudaSuccess) return CSDO_ERR_CUDA;
+  csdo_handle *h = new csdo_handle();
+  h->device = device;
+  if (params) h->P = *params; else csdo_default_params(&h->P);
+  if (h->P.osqp_max_iter < 1 || h->P.scaling < 0 || h->P.max_iter < 0) { delete h; return CSDO_ERR_INVALID; }
+  h->num_sms = prop.multiProcessorCount;
+  h->smem_limit = (int)prop.sharedMemPerBlockOptin;
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return CSDO_ERR_CUDA; }
+  *out = h;
+  return CSDO_OK;
+}
+
+void csdo_destroy(csdo_handle *h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  for (auto &b : h->stage) if (b.p) cudaFree(b.p);
+  if (h->scratch.p) cudaFree(h->scratch.p);
+  if (h->queue.p) cudaFree(h->queue.p);
+  if (h->step_cnt.p) cudaFree(h->step_cnt.p);
+  cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+const char *csdo_last_error(const csdo_handle *h) { return h ? h->err.c_str() : "null handle"; }
+
+int csdo_last_launch(const csdo_handle *h, csdo_launch_info *info) {
+  if (!h || !info) return CSDO_ERR_INVALID;
+  *info = h->last;
+  return CSDO_OK;
+}
+
+int csdo_refine_device(csdo_handle *h, const csdo_batch *in, csdo_result *out, int max_nt, int max_planes,
+                       void *cuda_stream) {
+  if (!h || !in || !out) return CSDO_ERR_INVALID;
+  cudaSetDevice(h->device);
+  DevBatch B = as_dev(in);
+  DevOut O{out->traj, out->corridors, out->status, out->sqp_iters, out->n_qp, out->admm_iters,
+           out->n_factor, out->objective, out->inst_status, out->inst_static_legal};
+  cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->stream;
+  return run_refine(h, B, O, max_nt, max_planes, s);
+}
+
+int csdo_refine(csdo_handle *h, const csdo_batch *in, csdo_result *out) {
+  if (!h || !in || !out) return CSDO_ERR_INVALID;
+  cudaSetDevice(h->device);
+  Meta m;
+  int rc = validate_host(h, in, true, m);
+  if (rc) return rc;
+  if (in->n_agents == 0) return CSDO_OK;
+  DevBatch B;
+  if ((rc = upload_batch(h, in, m, true, B))) return rc;
+  // processing order: longest problems first (unless the caller gave one)
+  std::vector<int> order(in->n_agents);
+  if (in->agent_order) std::copy(in->agent_order, in->agent_order + in->n_agents, order.begin());
+  else {
+    std::iota(order.begin(), order.end(), 0);
+    std::vector<int64_t> cost(in->n_agents);
+    for (int a = 0; a < in->n_agents; ++a)
+      cost[a] = 13 * (in->agent_off[a + 1] - in->agent_off[a]) + 4 * (int64_t)(in->plane_ptr[a + 1] - in->plane_ptr[a]);
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cost[x] > cost[y]; });
+  }
+  if ((rc = upload(h, 10, order.data(), order.size(), &B.agent_order))) return rc;
+  DevOut O;
+  const size_t A = in->n_agents, I = in->n_inst;
+  if ((rc = devalloc(h, 11, 6 * (size_t)m.steps, &O.traj))) return rc;
+  if ((rc = devalloc(h, 12, 8 * (size_t)m.steps, &O.corridors))) return rc;
+  int *ints = nullptr;
+  if ((rc = devalloc(h, 13, 5 * A + 2 * I, &ints))) return rc;
+  O.status = ints; O.sqp_iters = ints + A; O.n_qp = ints + 2 * A; O.admm_iters = ints + 3 * A;
+  O.n_factor = ints + 4 * A; O.inst_status = ints + 5 * A; O.inst_static_legal = ints + 5 * A + I;
+  if ((rc = devalloc(h, 14, A, &O.objective))) return rc;
+  if ((rc = run_refine(h, B, O, m.max_nt, m.max_k, h->stream))) return rc;
+  if ((rc = download(h, out->traj, O.traj, 6 * (size_t)m.steps))) return rc;
+  if ((rc = download(h, out->corridors, O.corridors, 8 * (size_t)m.steps))) return rc;
+  if ((rc = download(h, out->status, O.status, A))) return rc;
+  if ((rc = download(h, out->sqp_iters, O.sqp_iters, A))) return rc;
+  if ((rc = download(h, out->n_qp, O.n_qp, A))) return rc;
+  if ((rc = download(h, out->admm_iters, O.admm_iters, A))) return rc;
+  if ((rc = download(h, out->n_factor, O.n_factor, A))) return rc;
+  if ((rc = download(h, out->objective, O.objective, A))) return rc;
+  if ((rc = download(h, out->inst_status, O.inst_status, I))) return rc;
+  if ((rc = download(h, out->inst_static_legal, O.inst_static_legal, I))) return rc;
+  if (set_err(h, "refine", cudaStreamSynchronize(h->stream))) return CSDO_ERR_CUDA;
+  return CSDO_OK;
+}
+
+int csdo_corridors(csdo_handle *h, const csdo_batch *in, int double_centres, double *corridors,
+                   int32_t *box_status, int32_t *inst_static_legal) {
+  if (!h || !in || !corridors) return CSDO_ERR_INVALID;
+  cudaSetDevice(h->device);
+  Meta m;
+  int rc = validate_host(h, in, false, m);
+  if (rc) return rc;
+  if (in->n_agents == 0) return CSDO_OK;
+  DevBatch B;
+  if ((rc = upload_batch(h, in, m, false, B))) return rc;
+  double *d_corr; int *d_bs, *d_legal;
+  if ((rc = devalloc(h, 12, 8 * (size_t)m.steps, &d_corr))) return rc;
+  if ((rc = devalloc(h, 13, 4 * (size_t)m.steps + in->n_inst, &d_bs))) return rc;
+  d_legal = d_bs + 4 * (size_t)m.steps;
+  if (set_err(h, "launch_corridors", launch_corridors(B, h->P, double_centres, d_corr, d_bs, d_legal, h->stream)))
+    return CSDO_ERR_CUDA;
+  h->last.launches = 2;
+  if ((rc = download(h, corridors, d_corr, 8 * (size_t)m.steps))) return rc;
+  if ((rc = download(h, box_status, d_bs, 4 * (size_t)m.steps))) return rc;
+  if ((rc = download(h, inst_static_legal, d_legal, (size_t)in->n_inst))) return rc;
+  if (set_err(h, "corridors", cudaStreamSynchronize(h->stream))) return CSDO_ERR_CUDA;
+  return CSDO_OK;
+}
+
+int csdo_planes_count(csdo_handle *h, const csdo_batch *in, int32_t *plane_ptr, int32_t *inst_inter_legal) {
+  if (!h || !in || !plane_ptr) return CSDO_ERR_INVALID;
+  cudaSetDevice(h->device);
+  Meta m;
+  int rc = validate_host(h, in, false, m);
+  if (rc) return rc;
+  plane_ptr[0] = 0;
+  if (in->n_agents == 0) return CSDO_OK;
+  DevBatch B;
+  if ((rc = upload_batch(h, in, m, false, B))) return rc;
+  if ((rc = ensure(h, h->step_cnt, ((size_t)m.steps + in->n_inst + 1) * sizeof(int)))) return rc;
+  int *d_cnt = static_cast<int *>(h->step_cnt.p), *d_legal = d_cnt + m.steps;
+  if (set_err(h, "launch_planes_count", launch_planes_count(B, h->P, d_cnt, d_legal, h->stream))) return CSDO_ERR_CUDA;
+  std::vector<int> cnt((size_t)m.steps);
+  if ((rc = download(h, cnt.data(), d_cnt, (size_t)m.steps))) return rc;
+  if ((rc = download(h, inst_inter_legal, d_legal, (size_t)in->n_inst))) return rc;
+  if (set_err(h, "planes_count", cudaStreamSynchronize(h->stream))) return CSDO_ERR_CUDA;
+  // exclusive scan over (agent, step): plane index of the first plane of each step
+  int64_t run = 0;
+  for (int a = 0; a < in->n_agents; ++a) {
+    plane_ptr[a] = (int)run;
+    for (int64_t s = in->agent_off[a]; s < in->agent_off[a + 1]; ++s) { const int c = cnt[s]; cnt[s] = (int)run; run += c; }
+  }
+  plane_ptr[in->n_agents] = (int)run;
+  if (run > INT32_MAX) { h->err = "plane count overflows int32"; return CSDO_ERR_UNSUPPORTED; }
+  if (set_err(h, "cudaMemcpy step offsets",
+              cudaMemcpyAsync(d_cnt, cnt.data(), (size_t)m.steps * sizeof(int), cudaMemcpyHostToDevice, h->stream)))
+    return CSDO_ERR_CUDA;
+  if (set_err(h, "planes_count", cudaStreamSynchronize(h->stream))) return CSDO_ERR_CUDA;
+  h->last.launches = 2;
+  return CSDO_OK;
+}
+
+int csdo_planes_fill(csdo_handle *h, const csdo_batch *in, const int32_t *plane_ptr, int32_t *plane_t,
+                     double *plane_abc) {
+  if (!h || !in || !plane_ptr) return CSDO_ERR_INVALID;
+  cudaSetDevice(h->device);
+  Meta m;
+  int rc = validate_host(h, in, false, m);
+  if (rc) return rc;
+  if (in->n_agents == 0) return CSDO_OK;
+  const size_t total = (size_t)plane_ptr[in->n_agents];
+  if (total == 0) return CSDO_OK;
+  if (!plane_t || !plane_abc) return CSDO_ERR_INVALID;
+  if (h->step_cnt.cap < (size_t)m.steps * sizeof(int)) { h->err = "csdo_planes_count must precede csdo_planes_fill"; return CSDO_ERR_INVALID; }
+  DevBatch B;
+  if ((rc = upload_batch(h, in, m, false, B))) return rc;
+  int *d_t; double *d_abc;
+  if ((rc = devalloc(h, 8, total, &d_t))) return rc;
+  if ((rc = devalloc(h, 9, 12 * total, &d_abc))) return rc;
+  if (set_err(h, "launch_planes_fill",
+              launch_planes_fill(B, h->P, static_cast<int *>(h->step_cnt.p), d_t, d_abc, h->stream)))
+    return CSDO_ERR_CUDA;
+  h->last.launches = 1;
+  if ((rc = download(h, plane_t, d_t, total))) return rc;
+  if ((rc = download(h, plane_abc, d_abc, 12 * total))) return rc;
+  if (set_err(h, "planes_fill", cudaStreamSynchronize(h->stream))) return CSDO_ERR_CUDA;
+  return CSDO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,1099 @@
+// DSQP refine kernel for B200 (sm_100a): persistent CTAs, one agent per CTA at
+// a time, the agent's whole SQP loop on the device.  See dsqp_device.cuh for the
+// data layout.  Follows the reference's iterate sequence in FP64:
+//   SolverDSQP::calcIndividualSQP   sqp/dsqp_solver.cc:36-269
+//   solveOSQP -> OSQP 0.6.x ADMM    sqp/dsqp_solver.cc:423-555 (third-party solver,
+//                                   restated; see oracle/osqp_restate.c for the
+//                                   function-by-function correspondence)
+//   isFeasible / updateCorridor     sqp/dsqp_solver.cc:292-420, 818-872
+//   generateBox & co                sqp/corridor.cc:25-324
+#include "dsqp_device.cuh"
+#include "dsqp_launch.h"
+
+namespace csdo {
+
+// ===================================================================
+// corridor boxes (sqp/corridor.cc) -- adds/compares only, bit-exact
+// ===================================================================
+struct Box { double x_min, y_min, x_max, y_max; };
+
+struct ObsView {
+  const double *obs;  // [No][3]
+  int No;
+  double rv;
+};
+
+// isBoxValid :252-272 restricted to the candidate list (cand == nullptr: all)
+__device__ __forceinline__ bool box_valid(const Box &b, const ObsView &ov, const short *cand, int ncand,
+                                          double dimx, double dimy) {
+  const double rv = ov.rv;
+  if (b.x_min < rv || b.x_max > dimx - rv || b.y_min < rv || b.y_max > dimy - rv) return false;
+  const int n = cand ? ncand : ov.No;
+  for (int q = 0; q < n; ++q) {
+    const int o = cand ? cand[q] : q;
+    const double ox = ov.obs[3 * o], oy = ov.obs[3 * o + 1], R = ov.obs[3 * o + 2] + rv;
+    // Box::ExpandBox x4 (corridor.h:26-49): y_max+R, x_min-R, y_min-R, x_max+R
+    if (b.x_min - R < ox && ox < b.x_max + R && b.y_min - R < oy && oy < b.y_max + R) return false;
+  }
+  return true;
+}
+
+constexpr int kMaxCand = 40;
+
+// generateLocalBox :278-324.  Only obstacles that can ever touch a box grown
+// from (xc,yc) are kept as candidates (a conservative superset, so the
+// sequence of accepted expansions is unchanged).
+__device__ bool local_box(double xc, double yc, const ObsView &ov, double dimx, double dimy,
+                          const csdo_params &P, Box &res) {
+  short cand[kMaxCand];
+  int ncand = 0;
+  bool overflow = false;
+  const double reach = P.box_limit + 2.0 * P.box_ds + 1e-6;
+  for (int o = 0; o < ov.No; ++o) {
+    const double R = ov.obs[3 * o + 2] + ov.rv + reach;
+    if (fabs(ov.obs[3 * o] - xc) < R && fabs(ov.obs[3 * o + 1] - yc) < R) {
+      if (ncand < kMaxCand) cand[ncand++] = (short)o;
+      else overflow = true;
+    }
+  }
+  const short *cl = overflow ? nullptr : cand;
+  int id[4] = {0, 1, 2, 3};
+  double lens[4] = {0, 0, 0, 0};
+  Box box = {xc, yc, xc, yc};
+  int num_expand = 0, n_valid = 4;
+  while (n_valid > 0) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (id[k] == -1) continue;
+      Box tr = box;
+      if (k == 0) tr.y_max += P.box_ds;
+      else if (k == 1) tr.x_min -= P.box_ds;
+      else if (k == 2) tr.y_min -= P.box_ds;
+      else tr.x_max += P.box_ds;
+      if (box_valid(tr, ov, cl, ncand, dimx, dimy)) {
+        num_expand++;
+        lens[k] += P.box_ds;
+        box = tr;
+        if (lens[k] >= P.box_limit) { n_valid--; id[k] = -1; }
+      } else {
+        n_valid--; id[k] = -1;
+      }
+    }
+  }
+  res = box;
+  return num_expand > 0;
+}
+
+// generateBox :124-159 (+ isPointOutOfMap :25-30, projectNearBorder :54-81,
+// isPointCollision :32-52, generateLegalPoint :84-122)
+__device__ void generate_box(double x, double y, const ObsView &ov, double dimx, double dimy,
+                             const csdo_params &P, Box &box, int &success, int &initial) {
+  const double rv = ov.rv;
+  initial = 0;
+  box = Box{x, y, x, y};
+  if (x < rv || x > dimx - rv || y < rv || y > dimy - rv) {
+    initial = 1;
+    const double eps = 1e-3;
+    if (x < rv) x = rv + eps;
+    else if (x > dimx - rv) x = dimx - rv - eps;
+    if (y < rv) y = rv + eps;
+    else if (y > dimy - rv) y = dimy - rv - eps;
+  }
+  int oc = -1;
+  for (int o = 0; o < ov.No; ++o) {  // first hit in container order
+    const double ox = ov.obs[3 * o], oy = ov.obs[3 * o + 1], R = ov.obs[3 * o + 2] + rv;
+    if (x - R < ox && ox < x + R && y - R < oy && oy < y + R) { oc = o; break; }
+  }
+  if (oc < 0) {
+    success = local_box(x, y, ov, dimx, dimy, P, box) ? 1 : 0;
+    return;
+  }
+  initial = 2;
+  const double ocx = ov.obs[3 * oc], ocy = ov.obs[3 * oc + 1], ocr = ov.obs[3 * oc + 2];
+  const double theta0 = atan2(y - ocy, x - ocx);
+  const double d = rv + ocr + 0.2;
+  const int n_cand = 20;
+  for (int i = 0; i < n_cand; ++i) {
+    int j = i / 2;
+    if (i % 2 == 1) j = -j;
+    const double theta = __dadd_rn(theta0, j * 2 * M_PI / n_cand);
+    x = __dadd_rn(ocx, __dmul_rn(d, cos(theta)));
+    y = __dadd_rn(ocy, __dmul_rn(d, sin(theta)));
+    if (x > rv && x < dimx - rv && y > rv && y < dimy - rv) {
+      Box b = {0, 0, 0, 0};
+      local_box(x, y, ov, dimx, dimy, P, b);
+      if (box_valid(b, ov, nullptr, 0, dimx, dimy)) { box = b; success = 1; return; }
+    }
+  }
+  box = Box{x, y, x, y};
+  success = 0;
+}
+
+// calcCorridors (float centres) / updateCorridor (double centres) for the
+// agent of this CTA: 2 boxes per step, strided over the CTA's threads.
+__device__ int agent_corridors(const Ctx &c, const csdo_params &P, const double *xs, const double *ys,
+                               const double *yaws, int stride_is_nt, bool double_centres, int *box_status) {
+  (void)stride_is_nt;
+  ObsView ov{c.obs, c.No, P.rv};
+  int illegal = 0;
+  for (int b = c.tid; b < 2 * c.Nt; b += c.nthr) {
+    const int t = b >> 1, rear = b & 1;
+    const double off = rear ? P.r2x : P.f2x;
+    // separate multiply and add (the reference build has no FMA contraction)
+    double cx = __dadd_rn(xs[t], __dmul_rn(off, cos(yaws[t])));
+    double cy = __dadd_rn(ys[t], __dmul_rn(off, sin(yaws[t])));
+    if (!double_centres) {  // State members are float: motion_planning.h:115-118,230
+      cx = (double)(float)cx;
+      cy = (double)(float)cy;
+    }
+    Box bx; int ok, init;
+    generate_box(cx, cy, ov, c.dimx, c.dimy, P, bx, ok, init);
+    if (init > 0) illegal = 1;
+    const int base = rear ? 4 : 0;
+    c.corr[(base + 0) * c.Nt + t] = bx.x_min;
+    c.corr[(base + 1) * c.Nt + t] = bx.x_max;
+    c.corr[(base + 2) * c.Nt + t] = bx.y_min;
+    c.corr[(base + 3) * c.Nt + t] = bx.y_max;
+    if (box_status) { box_status[2 * b] = ok; box_status[2 * b + 1] = init; }
+  }
+  return illegal;
+}
+
+// ===================================================================
+// row functors
+// ===================================================================
+template <int NC>
+__device__ __forceinline__ double row_dot(const double (&v)[10], int i0, double c0, int i1, double c1, int i2,
+                                          double c2, int i3, double c3) {
+  double s = c0 * v[i0];
+  if (NC > 1) s += c1 * v[i1];
+  if (NC > 2) s += c2 * v[i2];
+  if (NC > 3) s += c3 * v[i3];
+  return s;
+}
+template <int NC>
+__device__ __forceinline__ void row_scatter(double (&acc)[10], double g, int i0, double c0, int i1, double c1,
+                                            int i2, double c2, int i3, double c3) {
+  acc[i0] += c0 * g;
+  if (NC > 1) acc[i1] += c1 * g;
+  if (NC > 2) acc[i2] += c2 * g;
+  if (NC > 3) acc[i3] += c3 * g;
+}
+
+// ADMM row update (OSQP update_xz_tilde/update_z/update_y folded on the single
+// state w = z_hat + y/rho: z = clip(w), y = rho (w - z)).
+//   MODE 0: warm start (osqp_warm_start_x: z = A x, y = 0)
+//   MODE 1: first iteration (z_prev is the unprojected A x)
+//   MODE 2: regular iteration
+//   MODE 3: re-base after a rho update (keeps z and y, osqp_update_rho)
+template <int MODE>
+struct StepF {
+  double xv[10];
+  double acc[10];
+  double alpha, rho, rho_old;
+  bool store_dy;
+  double *dy_base;       // shared-row delta_y (only kept when the agent has no planes)
+  const double *w_base;  // base of the shared w block
+  template <int NC>
+  __device__ __forceinline__ void row(int i0, double c0, int i1, double c1, int i2, double c2, int i3,
+                                      double c3, double l, double u, double &w, double &E) {
+    const double e = E;
+    const double ls = e * l, us = e * u;
+    const double rho_i = row_rho(ls, us, rho);
+    double wn, zn;
+    if (MODE == 0) {
+      wn = e * row_dot<NC>(xv, i0, c0, i1, c1, i2, c2, i3, c3);
+      zn = wn;
+    } else if (MODE == 3) {
+      const double wo = w, z = clipd(wo, ls, us);
+      const double rho_i_old = row_rho(ls, us, rho_old);
+      wn = z + (rho_i_old / rho_i) * (wo - z);
+      zn = z;
+    } else {
+      const double zt = e * row_dot<NC>(xv, i0, c0, i1, c1, i2, c2, i3, c3);
+      const double wo = w;
+      const double zo = (MODE == 1) ? wo : clipd(wo, ls, us);
+      const double yor = wo - zo;  // y_prev / rho
+      const double zhat = alpha * zt + (1.0 - alpha) * zo;
+      wn = zhat + yor;
+      zn = clipd(wn, ls, us);
+      if (store_dy) dy_base[&w - w_base] = rho_i * (zhat - zn);
+    }
+    w = wn;
+    const double g = e * (rho_i * (2.0 * zn - wn));  // E (rho z - y)
+    row_scatter<NC>(acc, g, i0, c0, i1, c1, i2, c2, i3, c3);
+  }
+};
+
+// residuals / norms (OSQP update_info, compute_pri_tol, compute_dua_tol,
+// is_primal_infeasible, compute_rho_estimate)
+enum Norm : int {
+  N_PRI_U = 0, N_Z_U, N_AX_U, N_PRI_S, N_Z_S, N_AX_S,  // rows
+  N_DUA_U, N_PX_U, N_ATY_U, N_DUA_S, N_PX_S, N_ATY_S,   // unknowns
+  N_DY, N_ATDY, N_COUNT
+};
+struct CheckF {
+  double xv[10];
+  double acc[10];   // A'y (raw-space accumulation)
+  double accd[10];  // A'delta_y
+  double nrm[N_COUNT];
+  double ineq_lhs;
+  double rho;
+  bool with_dy;
+  const double *dy_base;
+  const double *w_base;
+  template <int NC>
+  __device__ __forceinline__ void row(int i0, double c0, int i1, double c1, int i2, double c2, int i3,
+                                      double c3, double l, double u, double &w, double &E) {
+    const double e = E, einv = 1.0 / e;
+    const double ls = e * l, us = e * u;
+    const double rho_i = row_rho(ls, us, rho);
+    const double ax = e * row_dot<NC>(xv, i0, c0, i1, c1, i2, c2, i3, c3);
+    const double wv = w, z = clipd(wv, ls, us);
+    const double y = rho_i * (wv - z);
+    const double r = ax - z;
+    nrm[N_PRI_S] = fmax(nrm[N_PRI_S], fabs(r));
+    nrm[N_Z_S] = fmax(nrm[N_Z_S], fabs(z));
+    nrm[N_AX_S] = fmax(nrm[N_AX_S], fabs(ax));
+    nrm[N_PRI_U] = fmax(nrm[N_PRI_U], fabs(einv * r));
+    nrm[N_Z_U] = fmax(nrm[N_Z_U], fabs(einv * z));
+    nrm[N_AX_U] = fmax(nrm[N_AX_U], fabs(einv * ax));
+    row_scatter<NC>(acc, e * y, i0, c0, i1, c1, i2, c2, i3, c3);
+    if (with_dy) {
+      const double dy = dy_base[&w - w_base];
+      nrm[N_DY] = fmax(nrm[N_DY], fabs(e * dy));
+      ineq_lhs += us * (dy > 0 ? dy : 0) + ls * (dy < 0 ? dy : 0);
+      row_scatter<NC>(accd, e * dy, i0, c0, i1, c1, i2, c2, i3, c3);
+    }
+  }
+};
+
+// one Ruiz pass over the rows (OSQP scale_data): row norms -> E, column maxima
+struct ScaleF {
+  double dv[10];    // current D of the touched unknowns
+  double cmax[10];  // max_i E_i |a_ij| per touched unknown (without D_j)
+  template <int NC>
+  __device__ __forceinline__ void row(int i0, double c0, int i1, double c1, int i2, double c2, int i3,
+                                      double c3, double l, double u, double &w, double &E) {
+    const double e = E;
+    double rn = fabs(c0) * dv[i0];
+    cmax[i0] = fmax(cmax[i0], e * fabs(c0));
+    if (NC > 1) { rn = fmax(rn, fabs(c1) * dv[i1]); cmax[i1] = fmax(cmax[i1], e * fabs(c1)); }
+    if (NC > 2) { rn = fmax(rn, fabs(c2) * dv[i2]); cmax[i2] = fmax(cmax[i2], e * fabs(c2)); }
+    if (NC > 3) { rn = fmax(rn, fabs(c3) * dv[i3]); cmax[i3] = fmax(cmax[i3], e * fabs(c3)); }
+    rn = limit_scaling(e * rn);
+    E = e * (1.0 / sqrt(rn));
+  }
+};
+
+// reset E to 1 before scaling
+struct ResetF {
+  template <int NC>
+  __device__ __forceinline__ void row(int, double, int, double, int, double, int, double, double, double,
+                                      double &w, double &E) {
+    E = 1.0;
+    w = 0.0;
+  }
+};
+
+// A' diag(rho E^2) A in raw space: own 6x6 block (lower triangle), the coupling
+// to the next step and the next step's diagonal contributions.
+struct HasmF {
+  double q[6][6];   // q[i][j], j <= i
+  double cr[4][6];  // rows = next-step x,y,yaw,steer; cols = own unknowns
+  double nd[4];
+  double rho;
+  __device__ __forceinline__ void add(int i, int j, double v) {
+    if (i < j) { int s = i; i = j; j = s; }
+    if (i < 6) q[i][j] += v;
+    else if (j < 6) cr[i - 6][j] += v;
+    else nd[i - 6] += v;  // only i == j occurs
+  }
+  template <int NC>
+  __device__ __forceinline__ void row(int i0, double c0, int i1, double c1, int i2, double c2, int i3,
+                                      double c3, double l, double u, double &w, double &E) {
+    const double e = E;
+    const double h = row_rho(e * l, e * u, rho) * (e * e);
+    add(i0, i0, h * c0 * c0);
+    if (NC > 1) { add(i1, i0, h * c1 * c0); add(i1, i1, h * c1 * c1); }
+    if (NC > 2) { add(i2, i0, h * c2 * c0); add(i2, i1, h * c2 * c1); add(i2, i2, h * c2 * c2); }
+    if (NC > 3) { add(i3, i0, h * c3 * c0); add(i3, i1, h * c3 * c1); add(i3, i2, h * c3 * c2); add(i3, i3, h * c3 * c3); }
+  }
+};
+
+// ===================================================================
+// banded LDL' (round-1 version: the recurrences run on one thread)
+// ===================================================================
+__device__ __forceinline__ int vix(int i, int NT) { return (i % 6) * NT + (i / 6); }
+
+__device__ void band_factor_serial(double *L, int n) {
+  // in: L[i*7+0] = H_ii, L[i*7+d] = H_{i,i-d}; out: L[i*7+0] = 1/d_i, L[i*7+d] = l_{i,i-d}
+  for (int i = 0; i < n; ++i) {
+    double u[kLw];
+    double *Li = L + (size_t)i * kLw;
+#pragma unroll
+    for (int d = kBand; d >= 1; --d) {
+      const int j = i - d;
+      double s = 0.0;
+      if (j >= 0) {
+        s = Li[d];
+        const double *Lj = L + (size_t)j * kLw;
+#pragma unroll
+        for (int e = kBand; e > d; --e)
+          if (i - e >= 0) s -= u[e] * Lj[e - d];
+      }
+      u[d] = s;
+    }
+    double dsum = Li[0];
+#pragma unroll
+    for (int d = kBand; d >= 1; --d) {
+      const int j = i - d;
+      if (j >= 0) {
+        const double l = u[d] * L[(size_t)j * kLw];
+        dsum -= u[d] * l;
+        Li[d] = l;
+      }
+    }
+    Li[0] = 1.0 / dsum;
+  }
+}
+
+__device__ void band_solve_serial(const double *L, double *b, int n, int NT) {
+  // forward L y = b
+  for (int i = 0; i < n; ++i) {
+    const double *Li = L + (size_t)i * kLw;
+    double s = b[vix(i, NT)];
+#pragma unroll
+    for (int d = kBand; d >= 1; --d)
+      if (i - d >= 0) s -= Li[d] * b[vix(i - d, NT)];
+    b[vix(i, NT)] = s;
+  }
+  // D^-1 and backward L' x = y
+  for (int i = n - 1; i >= 0; --i) {
+    double s = b[vix(i, NT)] * L[(size_t)i * kLw];
+#pragma unroll
+    for (int d = 1; d <= kBand; ++d)
+      if (i + d < n) s -= L[(size_t)(i + d) * kLw + d] * b[vix(i + d, NT)];
+    b[vix(i, NT)] = s;
+  }
+}
+
+// ===================================================================
+// QP phases
+// ===================================================================
+__device__ __forceinline__ void load_xv(const Ctx &c, const double *v, double (&xv)[10]) {
+  const int NT = c.NT, t = c.t;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) xv[k] = v[k * NT + t];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) xv[6 + k] = c.has_next ? v[k * NT + t + 1] : 0.0;
+}
+
+// number of unknowns of step t (the last step has no v, w)
+__device__ __forceinline__ int nvar(const Ctx &c) { return c.has_next ? 6 : 4; }
+
+// linearization-dependent per-step data (dsqp_solver.cc:670-718, 893-948, 1116-1123)
+__device__ void assemble_rows(Ctx &c, const csdo_params &P) {
+  const int NT = c.NT, Nt = c.Nt, t = c.t;
+  if (c.active) {
+    const double yaw0 = c.cur[2 * NT + t], st0 = c.cur[3 * NT + t], v0 = c.cur[4 * NT + t];
+    const double sn = sin(yaw0), cs = cos(yaw0);
+    c.ro[RO_SN * NT + t] = sn;
+    c.ro[RO_CS * NT + t] = cs;
+    if (c.has_next) {
+      const double cd = cos(st0);
+      c.ro[RO_A1 * NT + t] = -P.dt * (v0 * sn);
+      c.ro[RO_A2 * NT + t] = P.dt * (v0 * cs);
+      c.ro[RO_A3 * NT + t] = (P.dt / P.WB * v0) / (cd * cd);
+      c.ro[RO_B3 * NT + t] = P.dt / P.WB * tan(st0);
+      c.ro[RO_KR0 * NT + t] = -(P.dt * yaw0 * v0 * sn);
+      c.ro[RO_KR1 * NT + t] = -(-P.dt * yaw0 * v0 * cs);
+      c.ro[RO_KR2 * NT + t] = -(-P.dt * (st0 * v0 / P.WB / (cd * cd)));
+    }
+    const double dxf = -P.f2x * sn, dyf = P.f2x * cs, dxr = -P.r2x * sn, dyr = P.r2x * cs;
+    const double exf = P.f2x * (cs + yaw0 * sn), eyf = P.f2x * (sn - yaw0 * cs);
+    const double exr = P.r2x * (cs + yaw0 * sn), eyr = P.r2x * (sn - yaw0 * cs);
+    c.ro[RO_CL0 * NT + t] = c.corr[0 * Nt + t] - exf; c.ro[RO_CU0 * NT + t] = c.corr[1 * Nt + t] - exf;
+    c.ro[RO_CL1 * NT + t] = c.corr[2 * Nt + t] - eyf; c.ro[RO_CU1 * NT + t] = c.corr[3 * Nt + t] - eyf;
+    c.ro[RO_CL2 * NT + t] = c.corr[4 * Nt + t] - exr; c.ro[RO_CU2 * NT + t] = c.corr[5 * Nt + t] - exr;
+    c.ro[RO_CL3 * NT + t] = c.corr[6 * Nt + t] - eyr; c.ro[RO_CU3 * NT + t] = c.corr[7 * Nt + t] - eyr;
+    for (int k = c.pstart[t]; k < c.pstart[t + 1]; ++k) {
+      const double *pl = c.plane_abc + (size_t)12 * k;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const double a = pl[3 * r], b = pl[3 * r + 1], cc = pl[3 * r + 2];
+        const double dx = r < 2 ? dxf : dxr, dy = r < 2 ? dyf : dyr;
+        const double ex = r < 2 ? exf : exr, ey = r < 2 ? eyf : eyr;
+        c.pl[PL_A * c.KP + 4 * k + r] = a * 1.0;
+        c.pl[PL_B * c.KP + 4 * k + r] = b * 1.0;
+        c.pl[PL_G * c.KP + 4 * k + r] = a * dx + b * dy;
+        c.pl[PL_U * c.KP + 4 * k + r] = -(cc + (a * ex + b * ey));
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// OSQP scale_data, `scaling` Ruiz passes; leaves D, E, c
+__device__ void ruiz_scale(Ctx &c, const csdo_params &P) {
+  const int NT = c.NT, t = c.t, Nt = c.Nt;
+  if (c.active) {
+    ResetF rf;
+    visit_rows(c, P, rf);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) c.D[k * NT + t] = 1.0;
+  }
+  c.c = 1.0;
+  __syncthreads();
+  for (int pass = 0; pass < P.scaling; ++pass) {
+    double dt_new[6];
+    if (c.active) {
+      ScaleF sf;
+      load_xv(c, c.D, sf.dv);
+#pragma unroll
+      for (int k = 0; k < 10; ++k) sf.cmax[k] = 0.0;
+      visit_rows(c, P, sf);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) c.carry[k * NT + t] = sf.cmax[6 + k];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) dt_new[k] = sf.cmax[k];
+    }
+    __syncthreads();
+    if (c.active) {
+      const int nv = nvar(c);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        if (k >= nv) continue;
+        const double dk = c.D[k * NT + t];
+        double a = dt_new[k];
+        if (k < 4 && t > 0) a = fmax(a, c.carry[k * NT + t - 1]);
+        double colA = a * dk;  // inf-norm of column k of the scaled A
+        double colP = 0.0;     // inf-norm of the column of the scaled (symmetric) P
+        if (k == VV) {
+          const double pv = (t != 0 && t != Nt - 2) ? 2.0 : 1.0;
+          colP = pv * dk;
+          if (t > 0) colP = fmax(colP, c.D[VV * NT + t - 1]);
+          if (t < Nt - 2) colP = fmax(colP, c.D[VV * NT + t + 1]);
+          colP = c.c * dk * colP;
+        } else if (k == VW) {
+          colP = c.c * dk * dk;
+        }
+        dt_new[k] = 1.0 / sqrt(limit_scaling(fmax(colP, colA)));
+      }
+    }
+    __syncthreads();
+    if (c.active) {
+      const int nv = nvar(c);
+#pragma unroll
+      for (int k = 0; k < 6; ++k)
+        if (k < nv) c.D[k * NT + t] *= dt_new[k];
+    }
+    __syncthreads();
+    // cost normalisation: mean column norm of the new P (q = 0 -> its norm counts as 1)
+    double s[1] = {0.0};
+    if (c.active && c.has_next) {
+      const double dvv = c.D[VV * NT + t], dw = c.D[VW * NT + t];
+      const double pv = (t != 0 && t != Nt - 2) ? 2.0 : 1.0;
+      double colP = pv * dvv;
+      if (t > 0) colP = fmax(colP, c.D[VV * NT + t - 1]);
+      if (t < Nt - 2) colP = fmax(colP, c.D[VV * NT + t + 1]);
+      s[0] = c.c * dvv * colP + c.c * dw * dw;
+    }
+    block_reduce<1, false>(s, c.red);
+    double c_temp = s[0] / (double)(6 * Nt - 2);
+    const double inf_norm_q = 1.0;  // limit_scaling(0) == 1
+    c_temp = fmax(c_temp, inf_norm_q);
+    c_temp = limit_scaling(c_temp);
+    c.c *= 1.0 / c_temp;
+  }
+}
+
+// reduced KKT  H = c D P D + sigma I + D A_raw' diag(rho E^2) A_raw D  into the
+// band storage, then LDL'.
+__device__ void form_and_factor(Ctx &c, const csdo_params &P) {
+  const int NT = c.NT, t = c.t, Nt = c.Nt;
+  HasmF hf;
+  if (c.active) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int j = 0; j < 6; ++j) hf.q[i][j] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      hf.nd[i] = 0.0;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) hf.cr[i][j] = 0.0;
+    }
+    hf.rho = c.rho;
+    visit_rows(c, P, hf);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) c.carry[k * NT + t] = hf.nd[k];
+    // clear this step's band rows
+    const int nv = nvar(c);
+    for (int k = 0; k < nv; ++k)
+#pragma unroll
+      for (int d = 0; d < kLw; ++d) c.L[(size_t)(6 * t + k) * kLw + d] = 0.0;
+  }
+  __syncthreads();
+  if (c.active) {
+    const int nv = nvar(c);
+    double dk[10];
+    load_xv(c, c.D, dk);
+    // objective (dsqp_solver.cc:163-197): second difference on v, identity on w
+    if (c.has_next) {
+      hf.q[VV][VV] += c.c * ((t != 0 && t != Nt - 2) ? 2.0 : 1.0);
+      hf.q[VW][VW] += c.c * 1.0;
+    }
+    for (int k = 0; k < nv; ++k) {
+      double *Lr = c.L + (size_t)(6 * t + k) * kLw;
+      double diag = hf.q[k][k];
+      if (k < 4 && t > 0) diag += c.carry[k * NT + t - 1];
+      Lr[0] = dk[k] * dk[k] * diag + P.sigma;
+      for (int j = 0; j < k; ++j) Lr[k - j] = dk[k] * dk[j] * hf.q[k][j];
+    }
+    if (c.has_next) {
+      const int nvn = (t + 1 < Nt - 1) ? 6 : 4;
+      for (int k = 0; k < 4; ++k) {  // rows x,y,yaw,steer of step t+1
+        double *Lr = c.L + (size_t)(6 * (t + 1) + k) * kLw;
+        for (int j = k; j < 6; ++j) Lr[6 + k - j] = dk[6 + k] * dk[j] * hf.cr[k][j];
+      }
+      if (nvn == 6) {  // v_{t+1} - v_t coupling of the objective
+        double *Lr = c.L + (size_t)(6 * (t + 1) + VV) * kLw;
+        Lr[6] = c.D[VV * NT + t + 1] * dk[VV] * (-c.c);
+      }
+    }
+  }
+  __syncthreads();
+  if (c.tid == 0) band_factor_serial(c.L, 6 * Nt - 2);
+  __syncthreads();
+}
+
+struct QpOut {
+  int status, iters, n_factor;
+};
+
+// rhs <- sigma x + D (acc + carry[t-1])   (q = 0)
+__device__ __forceinline__ void finish_rhs(const Ctx &c, const csdo_params &P, const double (&acc)[10]) {
+  const int NT = c.NT, t = c.t;
+  if (c.active) {
+    const int nv = nvar(c);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      if (k >= nv) continue;
+      double a = acc[k];
+      if (k < 4 && t > 0) a += c.carry[k * NT + t - 1];
+      c.rhs[k * NT + t] = P.sigma * c.x[k * NT + t] + c.D[k * NT + t] * a;
+    }
+  }
+}
+
+template <int MODE>
+__device__ void step_rows(Ctx &c, const csdo_params &P, bool store_dy, double rho_old) {
+  StepF<MODE> sf;
+  if (c.active) {
+    load_xv(c, c.xt, sf.xv);
+#pragma unroll
+    for (int k = 0; k < 10; ++k) sf.acc[k] = 0.0;
+    sf.alpha = P.alpha; sf.rho = c.rho; sf.rho_old = rho_old;
+    sf.store_dy = store_dy; sf.dy_base = c.dy; sf.w_base = c.w;
+    visit_rows(c, P, sf);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) c.carry[k * c.NT + c.t] = sf.acc[6 + k];
+  }
+  __syncthreads();
+  finish_rhs(c, P, sf.acc);
+  __syncthreads();
+}
+
+// OSQP update_info + check_termination(approximate = false/true) on the reduced scalars
+struct CheckOut {
+  double nrm[N_COUNT];
+  double ineq_lhs;
+};
+
+__device__ void check_rows(Ctx &c, const csdo_params &P, bool with_dy, CheckOut &co) {
+  const int NT = c.NT, t = c.t, Nt = c.Nt;
+  // xt <- D x (the current iterate, not x~)
+  if (c.active) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) c.xt[k * NT + t] = c.D[k * NT + t] * c.x[k * NT + t];
+  }
+  __syncthreads();
+  CheckF cf;
+#pragma unroll
+  for (int k = 0; k < N_COUNT; ++k) cf.nrm[k] = 0.0;
+  cf.ineq_lhs = 0.0;
+  if (c.active) {
+    load_xv(c, c.xt, cf.xv);
+#pragma unroll
+    for (int k = 0; k < 10; ++k) { cf.acc[k] = 0.0; cf.accd[k] = 0.0; }
+    cf.rho = c.rho; cf.with_dy = with_dy; cf.dy_base = c.dy; cf.w_base = c.w;
+    visit_rows(c, P, cf);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      c.carry[k * NT + t] = cf.acc[6 + k];
+      c.rhs[k * NT + t] = cf.accd[6 + k];  // rhs is rebuilt below, see caller
+    }
+  }
+  __syncthreads();
+  if (c.active) {
+    const int nv = nvar(c);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      if (k >= nv) continue;
+      const double dk = c.D[k * NT + t], dinv = 1.0 / dk;
+      double a = cf.acc[k], ad = cf.accd[k];
+      if (k < 4 && t > 0) { a += c.carry[k * NT + t - 1]; ad += c.rhs[k * NT + t - 1]; }
+      const double aty = dk * a;
+      double px = 0.0;
+      if (k == VV) {
+        const double pv = (t != 0 && t != Nt - 2) ? 2.0 : 1.0;
+        double sacc = pv * (dk * c.x[VV * NT + t]);
+        if (t > 0) sacc -= c.D[VV * NT + t - 1] * c.x[VV * NT + t - 1];
+        if (t < Nt - 2) sacc -= c.D[VV * NT + t + 1] * c.x[VV * NT + t + 1];
+        px = c.c * dk * sacc;
+      } else if (k == VW) {
+        px = c.c * dk * (dk * c.x[VW * NT + t]);
+      }
+      const double r = px + aty;
+      cf.nrm[N_DUA_S] = fmax(cf.nrm[N_DUA_S], fabs(r));
+      cf.nrm[N_PX_S] = fmax(cf.nrm[N_PX_S], fabs(px));
+      cf.nrm[N_ATY_S] = fmax(cf.nrm[N_ATY_S], fabs(aty));
+      cf.nrm[N_DUA_U] = fmax(cf.nrm[N_DUA_U], fabs(dinv * r));
+      cf.nrm[N_PX_U] = fmax(cf.nrm[N_PX_U], fabs(dinv * px));
+      cf.nrm[N_ATY_U] = fmax(cf.nrm[N_ATY_U], fabs(dinv * aty));
+      if (with_dy) cf.nrm[N_ATDY] = fmax(cf.nrm[N_ATDY], fabs(dinv * (dk * ad)));
+    }
+  }
+  __syncthreads();
+  block_reduce<N_COUNT, true>(cf.nrm, c.red);
+  double s[1] = {cf.ineq_lhs};
+  block_reduce<1, false>(s, c.red);
+#pragma unroll
+  for (int k = 0; k < N_COUNT; ++k) co.nrm[k] = cf.nrm[k];
+  co.ineq_lhs = s[0];
+}
+
+// check_termination (OSQP auxil.c); returns status or 0 when not terminated
+__device__ int termination_status(const Ctx &c, const csdo_params &P, const CheckOut &co, bool approximate) {
+  const double cinv = 1.0 / c.c;
+  double eps_abs = P.eps_abs, eps_rel = P.eps_rel, eps_pinf = P.eps_prim_inf;
+  const double pri_res = co.nrm[N_PRI_U], dua_res = cinv * co.nrm[N_DUA_U];
+  if (pri_res > kOsqpInfty || dua_res > kOsqpInfty) return CSDO_QP_NON_CVX;
+  if (approximate) { eps_abs *= 10; eps_rel *= 10; eps_pinf *= 10; }
+  const double eps_prim = eps_abs + eps_rel * fmax(co.nrm[N_Z_U], co.nrm[N_AX_U]);
+  bool prim_ok = false, prim_inf = false;
+  if (pri_res < eps_prim) prim_ok = true;
+  else if (c.K == 0) {
+    // is_primal_infeasible; with K > 0 every inter-vehicle row carries a true
+    // -inf lower bound and the support-function sum is NaN, so the test never fires
+    const double ndy = co.nrm[N_DY];
+    if (ndy > eps_pinf && co.ineq_lhs < -eps_pinf * ndy) prim_inf = co.nrm[N_ATDY] < eps_pinf * ndy;
+  }
+  const double eps_dual = eps_abs + eps_rel * (cinv * fmax(co.nrm[N_ATY_U], co.nrm[N_PX_U]));
+  const bool dual_ok = dua_res < eps_dual;  // q = 0: dual infeasibility cannot trigger
+  if (prim_ok && dual_ok) return approximate ? CSDO_QP_SOLVED_INACCURATE : CSDO_QP_SOLVED;
+  if (prim_inf) return approximate ? CSDO_QP_PRIMAL_INFEASIBLE_INACCURATE : CSDO_QP_PRIMAL_INFEASIBLE;
+  return 0;
+}
+
+// solveOSQP (dsqp_solver.cc:423-555): setup + warm start + ADMM; solution in c.sol
+__device__ QpOut solve_qp(Ctx &c, const csdo_params &P) {
+  const int NT = c.NT, t = c.t, Nt = c.Nt;
+  QpOut out{CSDO_QP_UNSOLVED, 0, 1};
+  ruiz_scale(c, P);
+  c.rho = fmin(fmax(P.rho, kRhoMin), kRhoMax);
+  form_and_factor(c, P);
+  // osqp_warm_start_x: x <- Dinv x0, z <- A x, y = 0
+  if (c.active) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const double dk = c.D[k * NT + t];
+      const double xs = c.cur[k * NT + t] * (1.0 / dk);
+      c.x[k * NT + t] = xs;
+      c.xt[k * NT + t] = dk * xs;
+    }
+  }
+  __syncthreads();
+  step_rows<0>(c, P, false, 0.0);
+  const bool keep_dy = (c.K == 0);
+  CheckOut co;
+  bool checked = false;
+  int iter = 0;
+  for (iter = 1; iter <= P.osqp_max_iter; ++iter) {
+    if (c.tid == 0) band_solve_serial(c.L, c.rhs, 6 * Nt - 2, NT);
+    __syncthreads();
+    if (c.active) {
+      const int nv = nvar(c);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        if (k >= nv) continue;
+        const double xtil = c.rhs[k * NT + t], xp = c.x[k * NT + t];
+        c.x[k * NT + t] = P.alpha * xtil + (1.0 - P.alpha) * xp;
+        c.xt[k * NT + t] = c.D[k * NT + t] * xtil;
+      }
+    }
+    __syncthreads();
+    const bool can_check = P.check_termination && (iter % P.check_termination == 0);
+    const bool store_dy = keep_dy && (can_check || iter == P.osqp_max_iter);
+    if (iter == 1) step_rows<1>(c, P, store_dy, 0.0);
+    else step_rows<2>(c, P, store_dy, 0.0);
+    checked = false;
+    const bool adapt = P.adaptive_rho && P.adaptive_rho_interval && (iter % P.adaptive_rho_interval == 0);
+    if (can_check || adapt) {
+      // check_rows borrows rhs/carry as scratch: save the next right-hand side in xt afterwards
+      double keep[6];
+      if (c.active)
+#pragma unroll
+        for (int k = 0; k < 6; ++k) keep[k] = c.rhs[k * NT + t];
+      __syncthreads();
+      check_rows(c, P, keep_dy && store_dy, co);
+      if (c.active)
+#pragma unroll
+        for (int k = 0; k < 6; ++k) c.rhs[k * NT + t] = keep[k];
+      __syncthreads();
+      checked = can_check;
+      if (can_check) {
+        const int st = termination_status(c, P, co, false);
+        if (st != 0) { out.status = st; break; }
+      }
+      if (adapt) {
+        // compute_rho_estimate / adapt_rho on the scaled residual norms
+        double pri = co.nrm[N_PRI_S], dua = co.nrm[N_DUA_S];
+        pri /= (fmax(co.nrm[N_Z_S], co.nrm[N_AX_S]) + 1e-10);
+        dua /= (fmax(co.nrm[N_ATY_S], co.nrm[N_PX_S]) + 1e-10);
+        double rho_new = c.rho * sqrt(pri / (dua + 1e-10));
+        rho_new = fmin(fmax(rho_new, kRhoMin), kRhoMax);
+        if (rho_new > c.rho * P.adaptive_rho_tolerance || rho_new < c.rho / P.adaptive_rho_tolerance) {
+          const double rho_old = c.rho;
+          c.rho = rho_new;
+          out.n_factor++;
+          form_and_factor(c, P);
+          step_rows<3>(c, P, false, rho_old);
+        }
+      }
+    }
+  }
+  if (iter > P.osqp_max_iter) iter = P.osqp_max_iter;
+  out.iters = iter;
+  if (out.status == CSDO_QP_UNSOLVED) {
+    if (!checked) {
+      double keep[6];
+      if (c.active)
+#pragma unroll
+        for (int k = 0; k < 6; ++k) keep[k] = c.rhs[k * NT + t];
+      __syncthreads();
+      check_rows(c, P, keep_dy, co);
+      if (c.active)
+#pragma unroll
+        for (int k = 0; k < 6; ++k) c.rhs[k * NT + t] = keep[k];
+      __syncthreads();
+      const int st = termination_status(c, P, co, false);
+      if (st != 0) out.status = st;
+    }
+    if (out.status == CSDO_QP_UNSOLVED) {
+      const int st = termination_status(c, P, co, true);
+      out.status = st != 0 ? st : CSDO_QP_MAX_ITER_REACHED;
+    }
+  }
+  // store_solution: x_out = D x for statuses that carry a solution, else keep solution0
+  const bool has_solution = !(out.status == CSDO_QP_PRIMAL_INFEASIBLE ||
+                              out.status == CSDO_QP_PRIMAL_INFEASIBLE_INACCURATE ||
+                              out.status == CSDO_QP_NON_CVX);
+  if (c.active) {
+    const int nv = nvar(c);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      double v = 0.0;
+      if (k < nv) v = (has_solution && abs(out.status) <= 2) ? c.D[k * NT + t] * c.x[k * NT + t] : c.cur[k * NT + t];
+      c.sol[k * NT + t] = v;
+    }
+  }
+  __syncthreads();
+  return out;
+}
+
+// isFeasible (dsqp_solver.cc:292-420), fully_check = false, on c.sol
+__device__ bool is_feasible(Ctx &c, const csdo_params &P) {
+  const int NT = c.NT, t = c.t, Nt = c.Nt;
+  double s[1] = {0.0};
+  double mx[2] = {0.0, 0.0};
+  if (c.active) {
+    const double x0 = c.sol[0 * NT + t], y0 = c.sol[1 * NT + t], yaw0 = c.sol[2 * NT + t];
+    const double cs = cos(yaw0), sn = sin(yaw0);
+    if (c.has_next) {
+      const double st0 = c.sol[3 * NT + t], v0 = c.sol[4 * NT + t], w0 = c.sol[5 * NT + t];
+      double a = x0 + v0 * cs * P.dt - c.sol[0 * NT + t + 1]; s[0] += a * a;
+      a = y0 + v0 * sn * P.dt - c.sol[1 * NT + t + 1]; s[0] += a * a;
+      a = yaw0 + v0 * tan(st0) / P.WB * P.dt - c.sol[2 * NT + t + 1]; s[0] += a * a;
+      a = st0 + w0 * P.dt - c.sol[3 * NT + t + 1]; s[0] += a * a;
+    }
+    const double Y[4] = {x0 + P.f2x * cs, y0 + P.f2x * sn, x0 + P.r2x * cs, y0 + P.r2x * sn};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const double lo = c.corr[(2 * q) * Nt + t], hi = c.corr[(2 * q + 1) * Nt + t];
+      if (!(lo <= Y[q])) mx[0] = fmax(mx[0], lo - Y[q]);
+      if (!(Y[q] <= hi)) mx[0] = fmax(mx[0], Y[q] - hi);
+    }
+    for (int k = c.pstart[t]; k < c.pstart[t + 1]; ++k) {
+      const double *pl = c.plane_abc + (size_t)12 * k;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const double res = r < 2 ? pl[3 * r] * Y[0] + pl[3 * r + 1] * Y[1] + pl[3 * r + 2]
+                                 : pl[3 * r] * Y[2] + pl[3 * r + 1] * Y[3] + pl[3 * r + 2];
+        if (res > 0) mx[1] = fmax(mx[1], res);
+      }
+    }
+  }
+  block_reduce<1, false>(s, c.red);
+  block_reduce<2, true>(mx, c.red);
+  const double err_kin = s[0] / (double)Nt;
+  return err_kin < 1e-2 && mx[1] < 1e-1 && mx[0] < 1e-1;
+}
+
+// ===================================================================
+// the kernel
+// ===================================================================
+__global__ void __launch_bounds__(kMaxThreads, 1)
+dsqp_refine_kernel(const DevBatch B, const DevOut O, const csdo_params P, const Layout LY, double *scratch,
+                   int *queue) {
+  extern __shared__ double smem[];
+  __shared__ int s_agent;
+  __shared__ int s_flag;
+  Ctx c;
+  c.NT = LY.NT; c.KP = 4 * LY.KMAX; c.tid = threadIdx.x; c.nthr = blockDim.x; c.t = threadIdx.x;
+  const int NT = c.NT;
+  double *slot = scratch + (size_t)blockIdx.x * LY.slot_doubles;
+  c.x = smem + LY.o_x; c.xt = smem + LY.o_xt; c.rhs = smem + LY.o_rhs; c.D = smem + LY.o_D;
+  c.carry = smem + LY.o_carry; c.w = smem + LY.o_w; c.cfgw = c.w + 13 * NT;
+  c.E = smem + LY.o_E; c.cfgE = c.E + 13 * NT; c.red = smem + LY.o_red;
+  c.pstart = reinterpret_cast<int *>(smem + LY.o_pstart);
+  c.L = LY.tier >= 2 ? slot + LY.g_L : smem + LY.o_L;
+  c.ro = LY.tier >= 1 ? slot + LY.g_ro : smem + LY.o_ro;
+  c.cur = slot + LY.g_cur; c.sol = slot + LY.g_sol; c.dy = slot + LY.g_dy; c.pl = slot + LY.g_pl;
+
+  for (;;) {
+    if (threadIdx.x == 0) s_agent = atomicAdd(queue, 1);
+    __syncthreads();
+    const int qi = s_agent;
+    __syncthreads();
+    if (qi >= B.n_agents) break;
+    const int a = B.agent_order ? B.agent_order[qi] : qi;
+    // instance of this agent: last i with inst_agent_ptr[i] <= a
+    int lo = 0, hi = B.n_inst;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (B.inst_agent_ptr[mid] <= a) lo = mid; else hi = mid;
+    }
+    const int inst = lo;
+    const int Nt = B.inst_nt[inst];
+    const int64_t off = B.agent_off[a];
+    c.Nt = Nt;
+    c.active = c.t < Nt;
+    c.has_next = c.t < Nt - 1;
+    c.K = B.plane_ptr[a + 1] - B.plane_ptr[a];
+    c.plane_t = B.plane_t + B.plane_ptr[a];
+    c.plane_abc = B.plane_abc + (size_t)12 * B.plane_ptr[a];
+    c.No = B.obs_ptr[inst + 1] - B.obs_ptr[inst];
+    c.obs = B.obs + (size_t)3 * B.obs_ptr[inst];
+    c.dimx = B.inst_dims[2 * inst]; c.dimy = B.inst_dims[2 * inst + 1];
+    c.guess = B.guess + 6 * off;
+    c.corr = O.corridors + 8 * off;
+    double *traj = O.traj + 6 * off;
+    // planes of each step: planes are sorted by t (inter_agent_cons.cc:26-31)
+    for (int tt = c.tid; tt <= Nt; tt += c.nthr) {
+      int l2 = 0, h2 = c.K;
+      while (l2 < h2) { const int mid = (l2 + h2) >> 1; if (c.plane_t[mid] < tt) l2 = mid + 1; else h2 = mid; }
+      c.pstart[tt] = l2;
+    }
+    // solution0 and the frozen trust centre (dsqp_solver.cc:56-63); cfg (utils.cc:115-120)
+    if (c.active) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        double v = c.guess[k * Nt + c.t];
+        if (k >= 4 && !c.has_next) v = 0.0;
+        c.cur[k * NT + c.t] = v;
+        c.sol[k * NT + c.t] = v;
+      }
+      c.ro[RO_TRX * NT + c.t] = c.guess[0 * Nt + c.t];
+      c.ro[RO_TRY * NT + c.t] = c.guess[1 * Nt + c.t];
+    }
+    c.cfg[0] = c.guess[0]; c.cfg[1] = c.guess[Nt - 1];
+    c.cfg[2] = c.guess[Nt]; c.cfg[3] = c.guess[2 * Nt - 1];
+    c.cfg[4] = c.guess[2 * Nt]; c.cfg[5] = c.guess[3 * Nt - 1];
+    if (threadIdx.x == 0) s_flag = 0;
+    __syncthreads();
+    // calcCorridors (dsqp_solver.cc:1154) on float disc centres
+    if (agent_corridors(c, P, c.guess, c.guess + Nt, c.guess + 2 * Nt, 1, false, nullptr)) s_flag = 1;
+    __syncthreads();
+    if (threadIdx.x == 0 && s_flag) atomicAnd(&O.inst_static_legal[inst], 0);
+    __syncthreads();
+
+    const double th = P.delta_solution_threshold;
+    double delta = th + 1;
+    int iter_count = 0, status = 1, admm = 0, nfac = 0;
+    while (delta > th && iter_count < P.max_iter) {
+      assemble_rows(c, P);
+      const QpOut q = solve_qp(c, P);
+      status = q.status; admm += q.iters; nfac += q.n_factor;
+      double s[1] = {0.0};
+      if (c.active) {
+        const int nv = nvar(c);
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+          if (k < nv) { const double d = c.sol[k * NT + c.t] - c.cur[k * NT + c.t]; s[0] += d * d; }
+      }
+      block_reduce<1, false>(s, c.red);
+      delta = s[0];
+      iter_count++;
+      if (iter_count > P.max_iter / 2 && is_feasible(c, P)) break;
+      if (c.active)
+#pragma unroll
+        for (int k = 0; k < 6; ++k) c.cur[k * NT + c.t] = c.sol[k * NT + c.t];
+      __syncthreads();
+      if (!P.fixed_corridor) {
+        agent_corridors(c, P, c.sol, c.sol + NT, c.sol + 2 * NT, 0, true, nullptr);
+        __syncthreads();
+      }
+    }
+    // extractSingleSolutionVec2OptRes + per-agent records
+    double ob[1] = {0.0};
+    if (c.active) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) traj[k * Nt + c.t] = c.sol[k * NT + c.t];
+      if (c.has_next) {
+        const double w0 = c.sol[5 * NT + c.t];
+        ob[0] = 0.5 * w0 * w0;
+        if (c.t + 1 < Nt - 1) {
+          const double dv = c.sol[4 * NT + c.t + 1] - c.sol[4 * NT + c.t];
+          ob[0] += 0.5 * dv * dv;
+        }
+      }
+    }
+    block_reduce<1, false>(ob, c.red);
+    if (threadIdx.x == 0) {
+      O.status[a] = status; O.sqp_iters[a] = iter_count; O.n_qp[a] = iter_count;
+      O.admm_iters[a] = admm; O.n_factor[a] = nfac; O.objective[a] = ob[0];
+    }
+    __syncthreads();
+  }
+}
+
+// status aggregation of SolverDSQP (dsqp_solver.cc:1224-1243), one thread per instance
+__global__ void aggregate_status_kernel(const DevBatch B, const DevOut O) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B.n_inst) return;
+  bool any = false;
+  int worst = 2;
+  for (int a = B.inst_agent_ptr[i]; a < B.inst_agent_ptr[i + 1]; ++a) {
+    const int s = O.status[a];
+    if (abs(s) > 1) { any = true; if (abs(s) > worst) worst = s; }
+  }
+  O.inst_status[i] = any ? worst : 1;
+}
+
+__global__ void fill_int_kernel(int *p, int n, int v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// corridors only (csdo_corridors): one CTA per agent
+__global__ void corridors_kernel(const DevBatch B, const csdo_params P, int double_centres, double *corridors,
+                                 int *box_status, int *inst_static_legal) {
+  __shared__ int s_flag;
+  const int a = blockIdx.x;
+  int lo = 0, hi = B.n_inst;
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (B.inst_agent_ptr[mid] <= a) lo = mid; else hi = mid; }
+  const int inst = lo, Nt = B.inst_nt[inst];
+  const int64_t off = B.agent_off[a];
+  Ctx c;
+  c.Nt = Nt; c.tid = threadIdx.x; c.nthr = blockDim.x;
+  c.No = B.obs_ptr[inst + 1] - B.obs_ptr[inst];
+  c.obs = B.obs + (size_t)3 * B.obs_ptr[inst];
+  c.dimx = B.inst_dims[2 * inst]; c.dimy = B.inst_dims[2 * inst + 1];
+  c.corr = corridors + 8 * off;
+  const double *g = B.guess + 6 * off;
+  if (threadIdx.x == 0) s_flag = 0;
+  __syncthreads();
+  if (agent_corridors(c, P, g, g + Nt, g + 2 * Nt, 1, double_centres != 0,
+                      box_status ? box_status + 4 * off : nullptr))
+    s_flag = 1;
+  __syncthreads();
+  if (threadIdx.x == 0 && s_flag) atomicAnd(&inst_static_legal[inst], 0);
+}
+
+// ===================================================================
+// host-side launchers (called from csdo_api.cpp through dsqp_launch.h)
+// ===================================================================
+Layout make_layout(int NT, int KMAX, int smem_limit_bytes, int *ctas_per_sm_out) {
+  Layout best{};
+  int best_ctas = -1;
+  for (int tier = 0; tier <= 2; ++tier) {
+    Layout l{};
+    l.NT = NT; l.KMAX = KMAX; l.tier = tier;
+    int o = 0;
+    auto take = [&](int n) { int r = o; o += (n + 1) & ~1; return r; };
+    l.o_x = take(6 * NT); l.o_xt = take(6 * NT); l.o_rhs = take(6 * NT); l.o_D = take(6 * NT);
+    l.o_carry = take(4 * NT); l.o_w = take(13 * NT + 8); l.o_E = take(13 * NT + 8);
+    l.o_red = take(32 * N_COUNT);
+    l.o_pstart = take((NT + 2 + 1) / 2);
+    l.o_L = tier < 2 ? take(kLw * 6 * NT) : 0;
+    l.o_ro = tier < 1 ? take(RO_COUNT * NT) : 0;
+    l.smem_doubles = o;
+    size_t g = 0;
+    auto gtake = [&](size_t n) { size_t r = g; g += (n + 1) & ~(size_t)1; return r; };
+    l.g_cur = gtake(6 * (size_t)NT); l.g_sol = gtake(6 * (size_t)NT); l.g_dy = gtake(13 * (size_t)NT + 8);
+    l.g_pl = gtake((size_t)PL_COUNT * 4 * KMAX);
+    l.g_ro = gtake((size_t)RO_COUNT * NT);
+    l.g_L = gtake((size_t)kLw * 6 * NT);
+    l.slot_doubles = g;
+    const int bytes = o * 8;
+    if (bytes + 1024 > smem_limit_bytes) continue;
+    int ctas = smem_limit_bytes / (bytes + 1024);
+    if (ctas > best_ctas) { best = l; best_ctas = ctas; }
+  }
+  if (ctas_per_sm_out) *ctas_per_sm_out = best_ctas;
+  if (best_ctas < 0) best.NT = 0;
+  return best;
+}
+
+cudaError_t launch_refine(const DevBatch &B, const DevOut &O, const csdo_params &P, const Layout &LY,
+                          double *scratch, int *queue, int grid, int block, cudaStream_t stream) {
+  const int smem = LY.smem_doubles * 8;
+  cudaError_t e = cudaFuncSetAttribute(dsqp_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(queue, 0, sizeof(int), stream);
+  if (e != cudaSuccess) return e;
+  const int fb = 256;
+  fill_int_kernel<<<(B.n_inst + fb - 1) / fb, fb, 0, stream>>>(O.inst_static_legal, B.n_inst, 1);
+  dsqp_refine_kernel<<<grid, block, smem, stream>>>(B, O, P, LY, scratch, queue);
+  aggregate_status_kernel<<<(B.n_inst + fb - 1) / fb, fb, 0, stream>>>(B, O);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_corridors(const DevBatch &B, const csdo_params &P, int double_centres, double *corridors,
+                             int *box_status, int *inst_static_legal, cudaStream_t stream) {
+  const int fb = 256;
+  fill_int_kernel<<<(B.n_inst + fb - 1) / fb, fb, 0, stream>>>(inst_static_legal, B.n_inst, 1);
+  corridors_kernel<<<B.n_agents, 128, 0, stream>>>(B, P, double_centres, corridors, box_status,
+                                                   inst_static_legal);
+  return cudaGetLastError();
+}
+
+int refine_occupancy(int block, int smem_bytes) {
+  if (cudaFuncSetAttribute(dsqp_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) !=
+      cudaSuccess)
+    return 0;
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, dsqp_refine_kernel, block, smem_bytes) != cudaSuccess)
+    return 0;
+  return n;
+}
+
+int refine_kernel_regs() {
+  cudaFuncAttributes fa;
+  if (cudaFuncGetAttributes(&fa, dsqp_refine_kernel) != cudaSuccess) return -1;
+  return fa.numRegs;
+}
+
+}  // namespace csdo

@@ -1,0 +1,56 @@
+// Host <-> kernel interface of the DSQP refine path (internal to the library).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "csdo_dsqp.h"
+
+namespace csdo {
+
+constexpr int kMaxThreads = 512;  // one thread per time step => horizon <= 512
+
+struct DevBatch {  // device pointers, same meaning as csdo_batch
+  int n_inst, n_agents;
+  const int *inst_agent_ptr, *inst_nt;
+  const double *inst_dims;
+  const int *obs_ptr;
+  const double *obs;
+  const int64_t *agent_off;
+  const double *guess;
+  const int *plane_ptr, *plane_t;
+  const double *plane_abc;
+  const int *agent_order;  // may be null
+};
+
+struct DevOut {  // device pointers, same meaning as csdo_result
+  double *traj, *corridors;
+  int *status, *sqp_iters, *n_qp, *admm_iters, *n_factor;
+  double *objective;
+  int *inst_status, *inst_static_legal;
+};
+
+// Shared-memory / scratch placement for one launch (offsets in doubles).
+struct Layout {
+  int NT, KMAX, tier, smem_doubles;
+  int o_x, o_xt, o_rhs, o_D, o_carry, o_w, o_E, o_red, o_pstart, o_L, o_ro;
+  size_t g_cur, g_sol, g_dy, g_pl, g_ro, g_L, slot_doubles;
+};
+
+Layout make_layout(int NT, int KMAX, int smem_limit_bytes, int *ctas_per_sm_out);
+int refine_occupancy(int block, int smem_bytes);
+int refine_kernel_regs();
+
+cudaError_t launch_refine(const DevBatch &B, const DevOut &O, const csdo_params &P, const Layout &LY,
+                          double *scratch, int *queue, int grid, int block, cudaStream_t stream);
+cudaError_t launch_corridors(const DevBatch &B, const csdo_params &P, int double_centres, double *corridors,
+                             int *box_status, int *inst_static_legal, cudaStream_t stream);
+
+// neighbour pairs + planes (planes_kernel.cu)
+cudaError_t launch_planes_count(const DevBatch &B, const csdo_params &P, int *step_cnt, int *inst_inter_legal,
+                                cudaStream_t stream);
+cudaError_t launch_planes_fill(const DevBatch &B, const csdo_params &P, const int *step_off, int *plane_t,
+                               double *plane_abc, cudaStream_t stream);
+
+}  // namespace csdo

@@ -149,7 +149,9 @@ def synthetic_instance(seed: int, size: float, n_agents: int, n_obs: int,
         if not (np.all(d > p.rv + 0.05) and np.all(d < size - p.rv - 0.05)):
             return False
         if obs.shape[0]:
-            dd = np.hypot(d[:, None, 0] - obs[None, :, 0], d[:, None, 1] - obs[None, :, 1])
+            # the reference's static test is an axis-aligned square of half-size r + rv
+            # around each obstacle (corridor.cc:32-52), hence the Chebyshev distance
+            dd = np.maximum(np.abs(d[:, None, 0] - obs[None, :, 0]), np.abs(d[:, None, 1] - obs[None, :, 1]))
             if np.any(dd < obs[None, :, 2] + clear_o):
                 return False
         for other in planned:
@@ -157,8 +159,6 @@ def synthetic_instance(seed: int, size: float, n_agents: int, n_obs: int,
             dd = np.hypot(d[:, None, 0] - o[None, :, 0], d[:, None, 1] - o[None, :, 1])
             if np.any(dd < clear_a):
                 return False
-            if step >= other.shape[0] - 1:
-                continue
         return True
 
     paths = []

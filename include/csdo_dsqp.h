@@ -114,6 +114,9 @@ typedef struct csdo_batch {
   const int32_t *plane_ptr;      /* [n_agents+1] */
   const int32_t *plane_t;        /* [sum K] */
   const double *plane_abc;       /* [sum K][12] */
+  const int32_t *agent_order;    /* [n_agents] optional processing order (a
+                                    permutation, longest first balances the
+                                    GPU best); NULL = the library decides */
 } csdo_batch;
 
 typedef struct csdo_result {
@@ -151,10 +154,14 @@ const char *csdo_last_error(const csdo_handle *h);
  */
 int csdo_refine(csdo_handle *h, const csdo_batch *in, csdo_result *out);
 
-/* Same, DEVICE pointers in both structs; enqueued on `cuda_stream` (a
- * cudaStream_t, 0 = the handle's stream); returns without synchronizing. */
+/* Same, but every pointer in both structs is a DEVICE pointer (inputs already
+ * resident in HBM, results stay there).  max_nt / max_planes: the largest
+ * horizon and the largest per-agent plane count of the batch (host ints, so
+ * no device->host read is needed to size the launch).  Enqueued on
+ * `cuda_stream` (a cudaStream_t; NULL = the handle's stream); returns without
+ * synchronizing. */
 int csdo_refine_device(csdo_handle *h, const csdo_batch *in, csdo_result *out,
-                       void *cuda_stream);
+                       int max_nt, int max_planes, void *cuda_stream);
 
 /* Kernel-launch and timing facts of the last refine on this handle
  * (launches: kernels enqueued; smem_bytes/block/grid: the DSQP kernel's
