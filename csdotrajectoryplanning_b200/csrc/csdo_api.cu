@@ -143,12 +143,19 @@ int run_refine(csdo_handle *h, const DevBatch &B, const DevOut &O, int max_nt, i
   if (max_nt > kMaxThreads) { h->err = "horizon exceeds 512 steps"; return CSDO_ERR_UNSUPPORTED; }
   const int NT = (max_nt + 31) & ~31;
   const int KMAX = std::max(4, (max_k + 3) & ~3);
-  int ctas_smem = 0;
-  Layout LY = make_layout(NT, KMAX, h->smem_limit, &ctas_smem);
-  if (LY.NT == 0) { h->err = "horizon does not fit the shared-memory layout"; return CSDO_ERR_UNSUPPORTED; }
+  // placement: keep the band factor in shared memory whenever it fits (tier 0: everything
+  // shared; tier 1: read-only row data in global); tier 2 (factor in global) only for long horizons
   const int block = std::max(64, NT);
-  int occ = refine_occupancy(block, LY.smem_doubles * 8);
-  if (occ < 1) { h->err = "kernel cannot be resident (registers/shared memory)"; return CSDO_ERR_CUDA; }
+  Layout LY{};
+  int occ = 0;
+  for (int tier = 0; tier <= 2; ++tier) {
+    if (tier == 2 && occ > 0) break;
+    const Layout l = make_layout(NT, KMAX, tier);
+    if (l.smem_doubles * 8 + 1024 > h->smem_limit) continue;
+    const int o = refine_occupancy(block, l.smem_doubles * 8);
+    if (o > occ) { occ = o; LY = l; }
+  }
+  if (occ < 1) { h->err = "horizon does not fit the kernel's shared-memory layout"; return CSDO_ERR_UNSUPPORTED; }
   const int grid = std::min(B.n_agents, h->num_sms * occ);
   int rc;
   if ((rc = ensure(h, h->scratch, (size_t)grid * LY.slot_doubles * sizeof(double)))) return rc;

@@ -1025,36 +1025,26 @@ __global__ void corridors_kernel(const DevBatch B, const csdo_params P, int doub
 // ===================================================================
 // host-side launchers (called from csdo_api.cpp through dsqp_launch.h)
 // ===================================================================
-Layout make_layout(int NT, int KMAX, int smem_limit_bytes, int *ctas_per_sm_out) {
-  Layout best{};
-  int best_ctas = -1;
-  for (int tier = 0; tier <= 2; ++tier) {
-    Layout l{};
-    l.NT = NT; l.KMAX = KMAX; l.tier = tier;
-    int o = 0;
-    auto take = [&](int n) { int r = o; o += (n + 1) & ~1; return r; };
-    l.o_x = take(6 * NT); l.o_xt = take(6 * NT); l.o_rhs = take(6 * NT); l.o_D = take(6 * NT);
-    l.o_carry = take(4 * NT); l.o_w = take(13 * NT + 8); l.o_E = take(13 * NT + 8);
-    l.o_red = take(32 * N_COUNT);
-    l.o_pstart = take((NT + 2 + 1) / 2);
-    l.o_L = tier < 2 ? take(kLw * 6 * NT) : 0;
-    l.o_ro = tier < 1 ? take(RO_COUNT * NT) : 0;
-    l.smem_doubles = o;
-    size_t g = 0;
-    auto gtake = [&](size_t n) { size_t r = g; g += (n + 1) & ~(size_t)1; return r; };
-    l.g_cur = gtake(6 * (size_t)NT); l.g_sol = gtake(6 * (size_t)NT); l.g_dy = gtake(13 * (size_t)NT + 8);
-    l.g_pl = gtake((size_t)PL_COUNT * 4 * KMAX);
-    l.g_ro = gtake((size_t)RO_COUNT * NT);
-    l.g_L = gtake((size_t)kLw * 6 * NT);
-    l.slot_doubles = g;
-    const int bytes = o * 8;
-    if (bytes + 1024 > smem_limit_bytes) continue;
-    int ctas = smem_limit_bytes / (bytes + 1024);
-    if (ctas > best_ctas) { best = l; best_ctas = ctas; }
-  }
-  if (ctas_per_sm_out) *ctas_per_sm_out = best_ctas;
-  if (best_ctas < 0) best.NT = 0;
-  return best;
+Layout make_layout(int NT, int KMAX, int tier) {
+  Layout l{};
+  l.NT = NT; l.KMAX = KMAX; l.tier = tier;
+  int o = 0;
+  auto take = [&](int n) { int r = o; o += (n + 1) & ~1; return r; };
+  l.o_x = take(6 * NT); l.o_xt = take(6 * NT); l.o_rhs = take(6 * NT); l.o_D = take(6 * NT);
+  l.o_carry = take(4 * NT); l.o_w = take(13 * NT + 8); l.o_E = take(13 * NT + 8);
+  l.o_red = take(32 * N_COUNT);
+  l.o_pstart = take((NT + 2 + 1) / 2);
+  l.o_L = tier < 2 ? take(kLw * 6 * NT) : 0;
+  l.o_ro = tier < 1 ? take(RO_COUNT * NT) : 0;
+  l.smem_doubles = o;
+  size_t g = 0;
+  auto gtake = [&](size_t n) { size_t r = g; g += (n + 1) & ~(size_t)1; return r; };
+  l.g_cur = gtake(6 * (size_t)NT); l.g_sol = gtake(6 * (size_t)NT); l.g_dy = gtake(13 * (size_t)NT + 8);
+  l.g_pl = gtake((size_t)PL_COUNT * 4 * KMAX);
+  l.g_ro = gtake((size_t)RO_COUNT * NT);
+  l.g_L = gtake((size_t)kLw * 6 * NT);
+  l.slot_doubles = g;
+  return l;
 }
 
 cudaError_t launch_refine(const DevBatch &B, const DevOut &O, const csdo_params &P, const Layout &LY,

@@ -38,7 +38,7 @@ struct Layout {
   size_t g_cur, g_sol, g_dy, g_pl, g_ro, g_L, slot_doubles;
 };
 
-Layout make_layout(int NT, int KMAX, int smem_limit_bytes, int *ctas_per_sm_out);
+Layout make_layout(int NT, int KMAX, int tier);
 int refine_occupancy(int block, int smem_bytes);
 int refine_kernel_regs();
 
