@@ -21,7 +21,7 @@ CSDO_OK, CSDO_ERR_INVALID, CSDO_ERR_CUDA, CSDO_ERR_UNSUPPORTED, CSDO_ERR_NOMEM =
 EXPORTS = [
     "csdo_default_params", "csdo_version", "csdo_create", "csdo_destroy", "csdo_last_error",
     "csdo_refine", "csdo_refine_device", "csdo_last_launch", "csdo_corridors",
-    "csdo_planes_count", "csdo_planes_fill",
+    "csdo_planes_count", "csdo_planes_fill", "csdo_measure_fp64_peak",
 ]
 
 _lib = None
@@ -64,5 +64,7 @@ def lib():
         L.csdo_planes_count.restype = C.c_int
         L.csdo_planes_fill.argtypes = [H, C.POINTER(CsdoBatch), C.c_void_p, C.c_void_p, C.c_void_p]
         L.csdo_planes_fill.restype = C.c_int
+        L.csdo_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
+        L.csdo_measure_fp64_peak.restype = C.c_int
         _lib = L
     return _lib

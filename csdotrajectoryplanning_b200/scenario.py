@@ -180,8 +180,12 @@ def synthetic_instance(seed: int, size: float, n_agents: int, n_obs: int,
                         states.append(nxt); acts.append(int(a)); cur = int(a)
                         break
                 else:
-                    ok = False
-                    break
+                    # blocked: wait in place (planner action 6) if that is collision free
+                    if state_ok(states[-1], k + 1):
+                        states.append(states[-1].copy()); acts.append(6)
+                    else:
+                        ok = False
+                        break
             if not ok and len(acts) < n_actions[0] // 2:
                 continue
             # the final pose is held for the rest of the horizon: check it stays clear

@@ -198,6 +198,14 @@ int csdo_planes_fill(csdo_handle *h, const csdo_batch *in,
                      const int32_t *plane_ptr, int32_t *plane_t,
                      double *plane_abc);
 
+/*
+ * Measurement helper (no reference counterpart): sustained FP64 FMA throughput
+ * of `device` in TFLOP/s from a register-resident DFMA microbenchmark.  It is
+ * the roofline denominator of the DSQP kernel, which is FP64-pipe bound, not
+ * HBM or tensor-core bound.
+ */
+int csdo_measure_fp64_peak(int device, double *tflops_out);
+
 #ifdef __cplusplus
 }
 #endif

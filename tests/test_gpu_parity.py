@@ -67,7 +67,13 @@ def test_corridors_bit_exact(oracle, params, solver, double_centres):
         nt = g.shape[1]
         ob = b.obs[3 * b.obs_ptr[i]:3 * b.obs_ptr[i + 1]].reshape(-1, 3)
         c0, s0, _ = oracle.agent_corridors(params, g[0], g[1], g[2], 50.0, 50.0, ob, double_centres)
-        assert np.array_equal(corr[8 * o:8 * (o + nt)].reshape(8, nt), c0)
+        c1 = corr[8 * o:8 * (o + nt)].reshape(8, nt)
+        if double_centres:
+            # full-double disc centres: CUDA and glibc sin/cos differ in the last ulp,
+            # the box is centre +- k*0.1 so the same ulp shows up; the expansion counts must agree
+            assert np.abs(c1 - c0).max() < 1e-12
+        else:
+            assert np.array_equal(c1, c0)   # float-rounded centres: bit-exact
         assert np.array_equal(bs[4 * o:4 * (o + nt)].reshape(nt, 2, 2), s0)
 
 
@@ -85,7 +91,8 @@ def test_corridors_illegal_starts(oracle, params, solver):
         c0, s0, _ = oracle.agent_corridors(params, g[a, 0], g[a, 1], g[a, 2], 50.0, 50.0, obs, False)
         assert np.array_equal(corr[8 * 4 * a:8 * 4 * (a + 1)].reshape(8, 4), c0)
         assert np.array_equal(bs[4 * 4 * a:4 * 4 * (a + 1)].reshape(4, 2, 2), s0)
-    assert bs.reshape(3, 4, 2, 2)[0, 0, 0, 1] == 1 and bs.reshape(3, 4, 2, 2)[1, 0, 0, 1] == 2
+    st = bs.reshape(3, 4, 2, 2)   # [agent][t][front/rear][success, initial_status]
+    assert st[0, 0, 1, 1] == 1 and st[1, 0, 0, 1] == 2 and np.all(st[2, :, :, 1] == 0)
 
 
 @pytest.mark.parametrize("seeds,na,no", [([51, 52, 53], 5, 12), ([61], 10, 25), ([71, 72], 4, 0)])

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     """include/*.h <-> libcsdo_dsqp.so: every declared entry point is exported."""
     from csdotrajectoryplanning_b200 import binding
     hdr = open(os.path.join(ROOT, "include", "csdo_dsqp.h")).read()
-    declared = sorted(set(re.findall(r"\b(csdo_[a-z_]+)\s*\(", hdr)))
+    declared = sorted(set(re.findall(r"\b(csdo_[a-z0-9_]+)\s*\(", hdr)))
     assert set(declared) == set(binding.EXPORTS)
     L = binding.lib()
     for name in declared:
