@@ -118,10 +118,11 @@ def cpu_sample(p, inst, target_s: float, nthreads: int):
     n_agents_target = max(probe.n_agents, int(target_s / max(per_agent, 1e-9)))
     chosen, tot = [], 0
     stride = max(1, len(inst) // 60)
-    for ins in (inst[::stride] + inst):     # spread over the shapes first
+    first = list(range(0, len(inst), stride))             # spread over the shapes first
+    for i in first + [i for i in range(len(inst)) if i % stride]:
         if tot >= n_agents_target:
             break
-        chosen.append(ins); tot += ins.n_agents
+        chosen.append(inst[i]); tot += inst[i].n_agents
     return pack_instances(chosen), len(chosen)
 
 
@@ -202,14 +203,17 @@ def main():
     # ---- device-resident arm ----
     db, dr = DeviceBatch(batch, dev), DeviceResult(batch, dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
-    stream = torch.cuda.current_stream()
+    # a dedicated non-default stream: the kernels and the timing events share it (stream handle 0
+    # would mean "the handle's own stream" to csdo_refine_device)
+    stream = torch.cuda.Stream(device=dev)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
 
     def one_step(e=None):
-        flush.fill_(1)                      # L2 flush between iterations (outside the events)
-        if e: e[0].record(stream)
-        solver.refine_device(db, dr, stream.cuda_stream)
-        if e: e[1].record(stream)
+        with torch.cuda.stream(stream):
+            flush.fill_(1)                  # L2 flush between iterations (outside the events)
+            if e: e[0].record(stream)
+            solver.refine_device(db, dr, stream.cuda_stream)
+            if e: e[1].record(stream)
 
     for _ in range(args.warmup):
         one_step()

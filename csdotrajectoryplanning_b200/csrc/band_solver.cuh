@@ -1,0 +1,358 @@
+// Horizon-partitioned LDL' of the reduced KKT matrix (block tridiagonal, 6x6
+// blocks, scalar half-bandwidth 6) and the matching solve, run by ONE warp.
+//
+// The Nt time blocks are cut into P <= 8 partitions separated by P-1 single
+// "separator" blocks (a nested-dissection ordering of the same matrix, so the
+// solve is still an exact direct solve; only rounding differs from a
+// sequential band factor):
+//     [interior_0][sep_0][interior_1][sep_1] ... [interior_{P-1}]
+// Lane p owns partition p.
+//   factor:  F1  banded LDL' of every interior (lanes in lockstep)
+//            F2  Schur complement of the separators, streamed per partition
+//            F3  dense inverse of the (6(P-1))^2 separator system (whole warp)
+//   solve :  S1  z_p = H_pp^-1 b_p                (forward + backward sweeps)
+//            S2  g = b_sep - coupling * z ; x_sep = Sinv g   (warp mat-vec)
+//            S3  x_p = H_pp^-1 (b_p - coupling * x_sep)      (two more sweeps)
+// The sweeps keep a 6-deep window in registers, so the loop-carried chain is
+// one DFMA per unknown; rows are 6 doubles (48 B, LDS.128-able), 1/d separate.
+//
+// Storage (time-major row i = 6 t + k):
+//   L6[i*6 + d-1]  = l_{i,i-d}, d = 1..6 (before factor: H_{i,i-d}); slots that
+//                    reach across a partition boundary keep the RAW coupling
+//                    entries H_{i,i-d}, which S2/S3/F2 read
+//   dinv[i]        = 1/d_i (before factor: H_ii); separator rows keep H_ii
+#pragma once
+
+#include "dsqp_device.cuh"
+
+namespace csdo {
+
+constexpr int kMaxP = 8;
+constexpr int kMaxNs = 6 * (kMaxP - 1);  // separator unknowns
+
+struct Parts {
+  int P, base, rem;
+  __device__ __forceinline__ int len(int p) const { return base + (p < rem ? 1 : 0); }
+  __device__ __forceinline__ int start(int p) const { return p * (base + 1) + (p < rem ? p : rem); }
+  __device__ __forceinline__ int sep(int j) const { return start(j) + len(j); }  // block index of separator j
+};
+
+__device__ __forceinline__ Parts make_parts(int Nt) {
+  Parts q;
+  int P = (Nt + 1) / 8;
+  P = P < 1 ? 1 : (P > kMaxP ? kMaxP : P);
+  q.P = P;
+  const int interior = Nt - (P - 1);
+  q.base = interior / P;
+  q.rem = interior % P;
+  return q;
+}
+
+// number of unknowns of block t
+__device__ __forceinline__ int blk_nv(int t, int Nt) { return t < Nt - 1 ? 6 : 4; }
+
+// ---- F1: interior banded LDL' of blocks [t0, t1) (columns before 6*t0 are ignored) ----
+__device__ __forceinline__ void interior_factor(double *__restrict__ L6, double *__restrict__ dinv, int t0, int t1,
+                                                int Nt) {
+  const int i0 = 6 * t0;
+  for (int t = t0; t < t1; ++t) {
+    const int nv = blk_nv(t, Nt);
+    for (int k = 0; k < nv; ++k) {
+      const int i = 6 * t + k;
+      double *Li = L6 + (size_t)i * 6;
+      double u[7];
+#pragma unroll
+      for (int d = 6; d >= 1; --d) {
+        const int j = i - d;
+        double s = 0.0;
+        if (j >= i0) {
+          s = Li[d - 1];
+          const double *Lj = L6 + (size_t)j * 6;
+#pragma unroll
+          for (int e = 6; e > d; --e)
+            if (i - e >= i0) s -= u[e] * Lj[e - d - 1];
+        }
+        u[d] = s;
+      }
+      double dsum = dinv[i];
+#pragma unroll
+      for (int d = 6; d >= 1; --d) {
+        const int j = i - d;
+        if (j >= i0) {
+          const double l = u[d] * dinv[j];
+          dsum -= u[d] * l;
+          Li[d - 1] = l;
+        }
+      }
+      dinv[i] = 1.0 / dsum;
+    }
+  }
+}
+
+// ---- sweeps: out = H_pp^-1 (in + adjustments) for blocks [t0, t1) ----
+// adj_first / adj_last are added to the right-hand side of the first / last block.
+__device__ __forceinline__ void interior_solve(const double *__restrict__ L6, const double *__restrict__ dinv,
+                                               const double *in, double *out, int t0, int t1, int Nt, int NT,
+                                               const double (&adj_first)[6], const double (&adj_last)[6]) {
+  // forward: L y = b, stores y * dinv
+  double prev[6] = {0, 0, 0, 0, 0, 0};
+  for (int t = t0; t < t1; ++t) {
+    const int nv = blk_nv(t, Nt);
+    double cur[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      double s = 0.0;
+      if (k < nv) {
+        s = in[k * NT + t];
+        if (t == t0) s += adj_first[k];
+        if (t == t1 - 1) s += adj_last[k];
+        const double *r = L6 + (size_t)(6 * t + k) * 6;
+#pragma unroll
+        for (int d = 6; d >= 1; --d) {
+          const double yv = (k - d >= 0) ? cur[k - d] : prev[6 + k - d];
+          s = fma(-r[d - 1], yv, s);
+        }
+        out[k * NT + t] = s * dinv[6 * t + k];
+      }
+      cur[k] = s;
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) prev[k] = cur[k];
+  }
+  // backward: L' x = D^-1 y in outer-product form (row i of L updates the 6 rows above it)
+  double a_cur[6];
+  {
+    const int t = t1 - 1;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) a_cur[k] = (k < blk_nv(t, Nt)) ? out[k * NT + t] : 0.0;
+  }
+  for (int t = t1 - 1; t >= t0; --t) {
+    const int nv = blk_nv(t, Nt);
+    double a_prev[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) a_prev[k] = (t > t0) ? out[k * NT + t - 1] : 0.0;
+#pragma unroll
+    for (int k = 5; k >= 0; --k) {
+      if (k < nv) {
+        const double xv = a_cur[k];
+        out[k * NT + t] = xv;
+        const double *r = L6 + (size_t)(6 * t + k) * 6;
+#pragma unroll
+        for (int d = 1; d <= 6; ++d) {
+          if (k - d >= 0) a_cur[k - d] = fma(-r[d - 1], xv, a_cur[k - d]);
+          else if (t > t0) a_prev[6 + k - d] = fma(-r[d - 1], xv, a_prev[6 + k - d]);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) a_cur[k] = a_prev[k];
+  }
+}
+
+// raw coupling H[(tr,kr)][(tr-1,kc)] stored in row (tr,kr) at d = 6 + kr - kc (kc >= kr)
+__device__ __forceinline__ double coupling(const double *L6, int tr, int kr, int kc) {
+  return L6[(size_t)(6 * tr + kr) * 6 + (6 + kr - kc) - 1];
+}
+
+// ---- F2: Schur complement contributions of partition p, streamed ----
+__device__ void schur_partition(const BandMem &bm, const Parts &pt, int p, int Nt) {
+  const double *L6 = bm.L6, *dinv = bm.dinv;
+  const int t0 = pt.start(p), t1 = t0 + pt.len(p);
+  double *GCC = bm.G + p * 78, *GBB = GCC + 21, *GBC = GBB + 21;
+  double win[6][6];  // win[a][k]: y of column a (coupling to previous separator unknown a) at the last block seen
+  double gcc[21];
+#pragma unroll
+  for (int q = 0; q < 21; ++q) gcc[q] = 0.0;
+  const bool has_prev = p > 0;
+  if (has_prev) {
+    double prev[6][6];
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+      for (int k = 0; k < 6; ++k) prev[a][k] = 0.0;
+    for (int t = t0; t < t1; ++t) {
+      const int nv = blk_nv(t, Nt);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const double *r = L6 + (size_t)(6 * t + k) * 6;
+        const double di = (k < nv) ? dinv[6 * t + k] : 0.0;
+        double ya[6];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+          double s = 0.0;
+          if (k < nv) {
+            if (t == t0 && a >= k) s = coupling(L6, t0, k, a);  // C column a, nonzero in the first block only
+#pragma unroll
+            for (int d = 6; d >= 1; --d) {
+              const double yv = (k - d >= 0) ? win[a][k - d] : prev[a][6 + k - d];
+              s = fma(-r[d - 1], yv, s);
+            }
+          }
+          win[a][k] = s;
+          ya[a] = s;
+        }
+        int q = 0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+#pragma unroll
+          for (int b = 0; b <= a; ++b) { gcc[q] = fma(ya[a] * di, ya[b], gcc[q]); ++q; }
+      }
+#pragma unroll
+      for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int k = 0; k < 6; ++k) prev[a][k] = win[a][k];
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 21; ++q) GCC[q] = gcc[q];
+  if (p < pt.P - 1) {
+    // B columns: coupling of the next separator (block T) to the last interior block T-1
+    const int T = t1, tl = t1 - 1;
+    double z[6][6];  // z[a][k]: L^-1 B' column a restricted to the last block
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        double s = (k >= a) ? coupling(L6, T, a, k) : 0.0;
+        const double *r = L6 + (size_t)(6 * tl + k) * 6;
+#pragma unroll
+        for (int d = 1; d <= 5; ++d)
+          if (k - d >= 0) s = fma(-r[d - 1], z[a][k - d], s);
+        z[a][k] = s;
+      }
+    int q = 0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+      for (int b = 0; b <= a; ++b) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) s = fma(z[a][k] * dinv[6 * tl + k], z[b][k], s);
+        GBB[q++] = s;
+      }
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+      for (int cc = 0; cc < 6; ++cc) {
+        double s = 0.0;
+        if (has_prev) {
+#pragma unroll
+          for (int k = 0; k < 6; ++k) s = fma(z[a][k] * dinv[6 * tl + k], win[cc][k], s);
+        }
+        GBC[a * 6 + cc] = s;  // (next separator unknown a) x (previous separator unknown cc)
+      }
+  }
+}
+
+// ---- whole factorization, executed by warp 0 (all 32 lanes call it) ----
+__device__ void band_factor_warp(const BandMem &bm, int Nt) {
+  const Parts pt = make_parts(Nt);
+  const int lane = threadIdx.x & 31;
+  if (lane < pt.P) interior_factor(bm.L6, bm.dinv, pt.start(lane), pt.start(lane) + pt.len(lane), Nt);
+  __syncwarp();
+  if (pt.P == 1) return;
+  if (lane < pt.P) schur_partition(bm, pt, lane, Nt);
+  __syncwarp();
+  // F3: assemble S (dense, symmetric) and invert it in place (Gauss-Jordan, SPD: no pivoting)
+  const int Ns = 6 * (pt.P - 1);
+  double *S = bm.Sinv;
+  for (int e = lane; e < Ns * Ns; e += 32) S[e] = 0.0;
+  __syncwarp();
+  for (int e = lane; e < (pt.P - 1) * 36; e += 32) {
+    const int j = e / 36, a = (e % 36) / 6, b = e % 6;  // separator j, entry (a, b) of its 6x6 blocks
+    const int T = pt.sep(j);
+    // diagonal block: H_TT - GBB(partition j) - GCC(partition j+1)
+    const int hi = a > b ? a : b, lo = a > b ? b : a;
+    double v = (a == b) ? bm.dinv[6 * T + a] : bm.L6[(size_t)(6 * T + hi) * 6 + (hi - lo) - 1];
+    const int q = hi * (hi + 1) / 2 + lo;
+    v -= bm.G[j * 78 + 21 + q];
+    v -= bm.G[(j + 1) * 78 + q];
+    S[(6 * j + a) * Ns + 6 * j + b] = v;
+    if (j > 0) {  // coupling to the previous separator through partition j: -GBC(partition j)
+      const double c = -bm.G[j * 78 + 42 + a * 6 + b];
+      S[(6 * j + a) * Ns + 6 * (j - 1) + b] = c;
+      S[(6 * (j - 1) + b) * Ns + 6 * j + a] = c;
+    }
+  }
+  __syncwarp();
+  double *prow = bm.sv + 2 * kMaxNs;
+  for (int piv = 0; piv < Ns; ++piv) {
+    const double d = 1.0 / S[piv * Ns + piv];
+    __syncwarp();
+    for (int cidx = lane; cidx < Ns; cidx += 32) prow[cidx] = (cidx == piv) ? d : S[piv * Ns + cidx] * d;
+    __syncwarp();
+    for (int r = lane; r < Ns; r += 32) {
+      if (r == piv) continue;
+      const double f = S[r * Ns + piv];
+      for (int cidx = 0; cidx < Ns; ++cidx)
+        S[r * Ns + cidx] = (cidx == piv) ? -f * d : fma(-f, prow[cidx], S[r * Ns + cidx]);
+    }
+    for (int cidx = lane; cidx < Ns; cidx += 32) S[piv * Ns + cidx] = prow[cidx];
+    __syncwarp();
+  }
+}
+
+// ---- solve H x = b: b in `rhs` (SoA, overwritten by x), `tmp` is a scratch vector; warp 0 ----
+__device__ void band_solve_warp(const BandMem &bm, double *rhs, double *tmp, int Nt, int NT) {
+  const Parts pt = make_parts(Nt);
+  const int lane = threadIdx.x & 31;
+  const double zero6[6] = {0, 0, 0, 0, 0, 0};
+  if (pt.P == 1) {
+    if (lane == 0) interior_solve(bm.L6, bm.dinv, rhs, rhs, 0, Nt, Nt, NT, zero6, zero6);
+    __syncwarp();
+    return;
+  }
+  const int t0 = pt.start(lane < pt.P ? lane : 0), t1 = t0 + pt.len(lane < pt.P ? lane : 0);
+  if (lane < pt.P) interior_solve(bm.L6, bm.dinv, rhs, tmp, t0, t1, Nt, NT, zero6, zero6);  // S1
+  __syncwarp();
+  const int Ns = 6 * (pt.P - 1);
+  double *g = bm.sv, *xs = bm.sv + kMaxNs;
+  for (int e = lane; e < Ns; e += 32) {  // S2: separator right-hand side
+    const int j = e / 6, k = e % 6, T = pt.sep(j);
+    double s = rhs[k * NT + T];
+#pragma unroll
+    for (int kc = 0; kc < 6; ++kc)
+      if (kc >= k) s = fma(-coupling(bm.L6, T, k, kc), tmp[kc * NT + T - 1], s);
+    const int nvn = blk_nv(T + 1, Nt);
+#pragma unroll
+    for (int kr = 0; kr < 6; ++kr)
+      if (kr <= k && kr < nvn) s = fma(-coupling(bm.L6, T + 1, kr, k), tmp[kr * NT + T + 1], s);
+    g[e] = s;
+  }
+  __syncwarp();
+  for (int r = lane; r < Ns; r += 32) {  // x_sep = Sinv g
+    double s0 = 0.0, s1 = 0.0;
+    const double *Sr = bm.Sinv + r * Ns;
+    int cidx = 0;
+    for (; cidx + 1 < Ns; cidx += 2) { s0 = fma(Sr[cidx], g[cidx], s0); s1 = fma(Sr[cidx + 1], g[cidx + 1], s1); }
+    if (cidx < Ns) s0 = fma(Sr[cidx], g[cidx], s0);
+    xs[r] = s0 + s1;
+  }
+  __syncwarp();
+  for (int e = lane; e < Ns; e += 32) rhs[(e % 6) * NT + pt.sep(e / 6)] = xs[e];
+  if (lane < pt.P) {  // S3: interiors with the separator solution moved to the right-hand side
+    double af[6] = {0, 0, 0, 0, 0, 0}, al[6] = {0, 0, 0, 0, 0, 0};
+    if (lane > 0) {  // rows of the first block couple to the previous separator
+      const double *xp = xs + 6 * (lane - 1);
+      const int nv = blk_nv(t0, Nt);
+#pragma unroll
+      for (int k = 0; k < 6; ++k)
+        if (k < nv)
+#pragma unroll
+          for (int kc = 0; kc < 6; ++kc)
+            if (kc >= k) af[k] = fma(-coupling(bm.L6, t0, k, kc), xp[kc], af[k]);
+    }
+    if (lane < pt.P - 1) {  // columns of the last block couple to the next separator's rows
+      const double *xn = xs + 6 * lane;
+#pragma unroll
+      for (int kc = 0; kc < 6; ++kc)
+#pragma unroll
+        for (int kr = 0; kr < 6; ++kr)
+          if (kr <= kc) al[kc] = fma(-coupling(bm.L6, t1, kr, kc), xn[kr], al[kc]);
+    }
+    interior_solve(bm.L6, bm.dinv, rhs, rhs, t0, t1, Nt, NT, af, al);
+  }
+  __syncwarp();
+}
+
+}  // namespace csdo

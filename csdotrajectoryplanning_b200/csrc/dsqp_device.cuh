@@ -34,6 +34,13 @@ enum Pl : int { PL_A = 0, PL_B, PL_G, PL_U, PL_E, PL_W, PL_COUNT };
 // local unknown indices inside visit_rows: own step 0..5, next step x,y,yaw,steer 6..9
 enum Var : int { VX = 0, VY, VP, VS, VV, VW, NX, NY, NP, NS };
 
+struct BandMem {
+  double *L6, *dinv;  // [(6t+k)*6 + d-1], [6t+k]; generic pointers (shared or global)
+  double *Sinv;       // dense inverse of the separator Schur complement (shared)
+  double *sv;         // 3 * kMaxNs scratch: g, x_sep, pivot row (shared)
+  double *G;          // factor-time scratch: per partition GCC[21] GBB[21] GBC[36] (shared)
+};
+
 struct Ctx {
   int Nt, NT, K, KP, No, tid, nthr, t;  // t = this thread's time step (tid), valid if tid < Nt
   bool active, has_next;
@@ -41,7 +48,7 @@ struct Ctx {
   double *x, *xt, *rhs, *D, *carry, *w, *E, *red;
   double *cfgw, *cfgE;  // 6 start/goal rows (contiguous after w / E)
   int *pstart;          // [Nt+1] first plane of each step
-  double *L;            // band factor, generic pointer (shared or global), [(6t+k)*7 + d]
+  BandMem bm;           // band factor storage (band_solver.cuh)
   double *ro;           // RO_COUNT planes, generic pointer
   // per-CTA global scratch
   double *cur, *sol, *dy, *pl;

@@ -8,6 +8,7 @@
 //   isFeasible / updateCorridor     sqp/dsqp_solver.cc:292-420, 818-872
 //   generateBox & co                sqp/corridor.cc:25-324
 #include "dsqp_device.cuh"
+#include "band_solver.cuh"
 #include "dsqp_launch.h"
 
 namespace csdo {
@@ -322,63 +323,6 @@ struct HasmF {
 };
 
 // ===================================================================
-// banded LDL' (round-1 version: the recurrences run on one thread)
-// ===================================================================
-__device__ __forceinline__ int vix(int i, int NT) { return (i % 6) * NT + (i / 6); }
-
-__device__ void band_factor_serial(double *L, int n) {
-  // in: L[i*7+0] = H_ii, L[i*7+d] = H_{i,i-d}; out: L[i*7+0] = 1/d_i, L[i*7+d] = l_{i,i-d}
-  for (int i = 0; i < n; ++i) {
-    double u[kLw];
-    double *Li = L + (size_t)i * kLw;
-#pragma unroll
-    for (int d = kBand; d >= 1; --d) {
-      const int j = i - d;
-      double s = 0.0;
-      if (j >= 0) {
-        s = Li[d];
-        const double *Lj = L + (size_t)j * kLw;
-#pragma unroll
-        for (int e = kBand; e > d; --e)
-          if (i - e >= 0) s -= u[e] * Lj[e - d];
-      }
-      u[d] = s;
-    }
-    double dsum = Li[0];
-#pragma unroll
-    for (int d = kBand; d >= 1; --d) {
-      const int j = i - d;
-      if (j >= 0) {
-        const double l = u[d] * L[(size_t)j * kLw];
-        dsum -= u[d] * l;
-        Li[d] = l;
-      }
-    }
-    Li[0] = 1.0 / dsum;
-  }
-}
-
-__device__ void band_solve_serial(const double *L, double *b, int n, int NT) {
-  // forward L y = b
-  for (int i = 0; i < n; ++i) {
-    const double *Li = L + (size_t)i * kLw;
-    double s = b[vix(i, NT)];
-#pragma unroll
-    for (int d = kBand; d >= 1; --d)
-      if (i - d >= 0) s -= Li[d] * b[vix(i - d, NT)];
-    b[vix(i, NT)] = s;
-  }
-  // D^-1 and backward L' x = y
-  for (int i = n - 1; i >= 0; --i) {
-    double s = b[vix(i, NT)] * L[(size_t)i * kLw];
-#pragma unroll
-    for (int d = 1; d <= kBand; ++d)
-      if (i + d < n) s -= L[(size_t)(i + d) * kLw + d] * b[vix(i + d, NT)];
-    b[vix(i, NT)] = s;
-  }
-}
-
-// ===================================================================
 // QP phases
 // ===================================================================
 __device__ __forceinline__ void load_xv(const Ctx &c, const double *v, double (&xv)[10]) {
@@ -530,9 +474,11 @@ __device__ void form_and_factor(Ctx &c, const csdo_params &P) {
     for (int k = 0; k < 4; ++k) c.carry[k * NT + t] = hf.nd[k];
     // clear this step's band rows
     const int nv = nvar(c);
-    for (int k = 0; k < nv; ++k)
+    for (int k = 0; k < nv; ++k) {
 #pragma unroll
-      for (int d = 0; d < kLw; ++d) c.L[(size_t)(6 * t + k) * kLw + d] = 0.0;
+      for (int d = 0; d < 6; ++d) c.bm.L6[(size_t)(6 * t + k) * 6 + d] = 0.0;
+      c.bm.dinv[6 * t + k] = 0.0;
+    }
   }
   __syncthreads();
   if (c.active) {
@@ -545,26 +491,26 @@ __device__ void form_and_factor(Ctx &c, const csdo_params &P) {
       hf.q[VW][VW] += c.c * 1.0;
     }
     for (int k = 0; k < nv; ++k) {
-      double *Lr = c.L + (size_t)(6 * t + k) * kLw;
+      double *Lr = c.bm.L6 + (size_t)(6 * t + k) * 6 - 1;  // Lr[d] = H_{i,i-d}
       double diag = hf.q[k][k];
       if (k < 4 && t > 0) diag += c.carry[k * NT + t - 1];
-      Lr[0] = dk[k] * dk[k] * diag + P.sigma;
+      c.bm.dinv[6 * t + k] = dk[k] * dk[k] * diag + P.sigma;
       for (int j = 0; j < k; ++j) Lr[k - j] = dk[k] * dk[j] * hf.q[k][j];
     }
     if (c.has_next) {
       const int nvn = (t + 1 < Nt - 1) ? 6 : 4;
       for (int k = 0; k < 4; ++k) {  // rows x,y,yaw,steer of step t+1
-        double *Lr = c.L + (size_t)(6 * (t + 1) + k) * kLw;
+        double *Lr = c.bm.L6 + (size_t)(6 * (t + 1) + k) * 6 - 1;
         for (int j = k; j < 6; ++j) Lr[6 + k - j] = dk[6 + k] * dk[j] * hf.cr[k][j];
       }
       if (nvn == 6) {  // v_{t+1} - v_t coupling of the objective
-        double *Lr = c.L + (size_t)(6 * (t + 1) + VV) * kLw;
+        double *Lr = c.bm.L6 + (size_t)(6 * (t + 1) + VV) * 6 - 1;
         Lr[6] = c.D[VV * NT + t + 1] * dk[VV] * (-c.c);
       }
     }
   }
   __syncthreads();
-  if (c.tid == 0) band_factor_serial(c.L, 6 * Nt - 2);
+  if (c.tid < 32) band_factor_warp(c.bm, Nt);
   __syncthreads();
 }
 
@@ -721,7 +667,7 @@ __device__ QpOut solve_qp(Ctx &c, const csdo_params &P) {
   bool checked = false;
   int iter = 0;
   for (iter = 1; iter <= P.osqp_max_iter; ++iter) {
-    if (c.tid == 0) band_solve_serial(c.L, c.rhs, 6 * Nt - 2, NT);
+    if (c.tid < 32) band_solve_warp(c.bm, c.rhs, c.xt, Nt, NT);
     __syncthreads();
     if (c.active) {
       const int nv = nvar(c);
@@ -868,7 +814,11 @@ dsqp_refine_kernel(const DevBatch B, const DevOut O, const csdo_params P, const 
   c.carry = smem + LY.o_carry; c.w = smem + LY.o_w; c.cfgw = c.w + 13 * NT;
   c.E = smem + LY.o_E; c.cfgE = c.E + 13 * NT; c.red = smem + LY.o_red;
   c.pstart = reinterpret_cast<int *>(smem + LY.o_pstart);
-  c.L = LY.tier >= 2 ? slot + LY.g_L : smem + LY.o_L;
+  c.bm.L6 = LY.tier >= 2 ? slot + LY.g_L : smem + LY.o_L;
+  c.bm.dinv = c.bm.L6 + 36 * NT;
+  c.bm.Sinv = smem + LY.o_sinv;
+  c.bm.sv = c.bm.Sinv + kMaxNs * kMaxNs;
+  c.bm.G = c.xt;  // xt and rhs are contiguous and free while a factorization runs
   c.ro = LY.tier >= 1 ? slot + LY.g_ro : smem + LY.o_ro;
   c.cur = slot + LY.g_cur; c.sol = slot + LY.g_sol; c.dy = slot + LY.g_dy; c.pl = slot + LY.g_pl;
 
@@ -1034,6 +984,7 @@ Layout make_layout(int NT, int KMAX, int tier) {
   l.o_carry = take(4 * NT); l.o_w = take(13 * NT + 8); l.o_E = take(13 * NT + 8);
   l.o_red = take(32 * N_COUNT);
   l.o_pstart = take((NT + 2 + 1) / 2);
+  l.o_sinv = take(kMaxNs * kMaxNs + 3 * kMaxNs);
   l.o_L = tier < 2 ? take(kLw * 6 * NT) : 0;
   l.o_ro = tier < 1 ? take(RO_COUNT * NT) : 0;
   l.smem_doubles = o;

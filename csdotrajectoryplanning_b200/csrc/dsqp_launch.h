@@ -34,7 +34,7 @@ struct DevOut {  // device pointers, same meaning as csdo_result
 // Shared-memory / scratch placement for one launch (offsets in doubles).
 struct Layout {
   int NT, KMAX, tier, smem_doubles;
-  int o_x, o_xt, o_rhs, o_D, o_carry, o_w, o_E, o_red, o_pstart, o_L, o_ro;
+  int o_x, o_xt, o_rhs, o_D, o_carry, o_w, o_E, o_red, o_pstart, o_L, o_ro, o_sinv;
   size_t g_cur, g_sol, g_dy, g_pl, g_ro, g_L, slot_doubles;
 };
 
