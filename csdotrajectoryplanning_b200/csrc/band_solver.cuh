@@ -13,10 +13,14 @@
 //   solve :  S1  z_p = H_pp^-1 b_p                (forward + backward sweeps)
 //            S2  g = b_sep - coupling * z ; x_sep = Sinv g   (warp mat-vec)
 //            S3  x_p = H_pp^-1 (b_p - coupling * x_sep)      (two more sweeps)
-// The sweeps keep a 6-deep window in registers, so the loop-carried chain is
-// one DFMA per unknown; rows are 6 doubles (48 B, LDS.128-able), 1/d separate.
+// A sweep step handles one 6x6 block from registers: the part that depends on
+// the neighbouring block is 6 independent DFMA chains, the intra-block triangle
+// runs in outer-product order, so the loop-carried chain is ~6 DFMAs per block
+// and the step is bound by the issue rate of one warp (measured, see
+// scripts/micro/sweep_bench.cu).
 //
-// Storage (time-major row i = 6 t + k):
+// Storage (time-major row i = 6 t + k; every block has 6 rows -- the last time
+// step's missing v, w are dummy unknowns with H_ii = 1 and zero coupling):
 //   L6[i*6 + d-1]  = l_{i,i-d}, d = 1..6 (before factor: H_{i,i-d}); slots that
 //                    reach across a partition boundary keep the RAW coupling
 //                    entries H_{i,i-d}, which S2/S3/F2 read
@@ -26,6 +30,9 @@
 #include "dsqp_device.cuh"
 
 namespace csdo {
+
+__device__ unsigned long long g_dbg[16];  // developer counters (CSDO_PROFILE)
+#define DBG_T(i) do { if (lane == 0) { long long t_ = clock64(); atomicAdd(&g_dbg[i], (unsigned long long)(t_ - dbg_t0)); dbg_t0 = t_; } } while (0)
 
 constexpr int kMaxP = 8;
 constexpr int kMaxNs = 6 * (kMaxP - 1);  // separator unknowns
@@ -48,100 +55,92 @@ __device__ __forceinline__ Parts make_parts(int Nt) {
   return q;
 }
 
-// number of unknowns of block t
-__device__ __forceinline__ int blk_nv(int t, int Nt) { return t < Nt - 1 ? 6 : 4; }
-
 // ---- F1: interior banded LDL' of blocks [t0, t1) (columns before 6*t0 are ignored) ----
-__device__ __forceinline__ void interior_factor(double *__restrict__ L6, double *__restrict__ dinv, int t0, int t1,
-                                                int Nt) {
+__device__ __forceinline__ void interior_factor(double *__restrict__ L6, double *__restrict__ dinv, int t0, int t1) {
   const int i0 = 6 * t0;
-  for (int t = t0; t < t1; ++t) {
-    const int nv = blk_nv(t, Nt);
-    for (int k = 0; k < nv; ++k) {
-      const int i = 6 * t + k;
-      double *Li = L6 + (size_t)i * 6;
-      double u[7];
+  for (int i = i0; i < 6 * t1; ++i) {
+    double *Li = L6 + (size_t)i * 6;
+    double u[7];
 #pragma unroll
-      for (int d = 6; d >= 1; --d) {
-        const int j = i - d;
-        double s = 0.0;
-        if (j >= i0) {
-          s = Li[d - 1];
-          const double *Lj = L6 + (size_t)j * 6;
+    for (int d = 6; d >= 1; --d) {
+      const int j = i - d;
+      double s = 0.0;
+      if (j >= i0) {
+        s = Li[d - 1];
+        const double *Lj = L6 + (size_t)j * 6;
 #pragma unroll
-          for (int e = 6; e > d; --e)
-            if (i - e >= i0) s -= u[e] * Lj[e - d - 1];
-        }
-        u[d] = s;
+        for (int e = 6; e > d; --e)
+          if (i - e >= i0) s -= u[e] * Lj[e - d - 1];
       }
-      double dsum = dinv[i];
-#pragma unroll
-      for (int d = 6; d >= 1; --d) {
-        const int j = i - d;
-        if (j >= i0) {
-          const double l = u[d] * dinv[j];
-          dsum -= u[d] * l;
-          Li[d - 1] = l;
-        }
-      }
-      dinv[i] = 1.0 / dsum;
+      u[d] = s;
     }
+    double dsum = dinv[i];
+#pragma unroll
+    for (int d = 6; d >= 1; --d) {
+      const int j = i - d;
+      if (j >= i0) {
+        const double l = u[d] * dinv[j];
+        dsum -= u[d] * l;
+        Li[d - 1] = l;
+      }
+    }
+    dinv[i] = 1.0 / dsum;
   }
 }
 
-// ---- sweeps: out = H_pp^-1 (in + adjustments) for blocks [t0, t1) ----
-// adj_first / adj_last are added to the right-hand side of the first / last block.
+// ---- sweeps: out = H_pp^-1 in for blocks [t0, t1) ----
+__device__ __forceinline__ void load_rows(const double *__restrict__ L6, int t, double (&Lr)[6][6]) {
+  const double2 *r2 = reinterpret_cast<const double2 *>(L6 + (size_t)36 * t);
+#pragma unroll
+  for (int k = 0; k < 6; ++k)
+#pragma unroll
+    for (int h = 0; h < 3; ++h) {
+      const double2 v = r2[3 * k + h];
+      Lr[k][2 * h] = v.x;
+      Lr[k][2 * h + 1] = v.y;
+    }
+}
+
 __device__ __forceinline__ void interior_solve(const double *__restrict__ L6, const double *__restrict__ dinv,
-                                               const double *in, double *out, int t0, int t1, int Nt, int NT,
-                                               const double (&adj_first)[6], const double (&adj_last)[6]) {
+                                               const double *in, double *out, int t0, int t1, int NT) {
   // forward: L y = b, stores y * dinv
   double prev[6] = {0, 0, 0, 0, 0, 0};
   for (int t = t0; t < t1; ++t) {
-    const int nv = blk_nv(t, Nt);
-    double cur[6];
+    double Lr[6][6], p[6], dv[6];
+    load_rows(L6, t, Lr);
 #pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      double s = 0.0;
-      if (k < nv) {
-        s = in[k * NT + t];
-        if (t == t0) s += adj_first[k];
-        if (t == t1 - 1) s += adj_last[k];
-        const double *r = L6 + (size_t)(6 * t + k) * 6;
+    for (int k = 0; k < 6; ++k) { p[k] = in[k * NT + t]; dv[k] = dinv[6 * t + k]; }
+    // the part that only needs the previous block: row k uses d = k+1..6 -> prev[6+k-d]
 #pragma unroll
-        for (int d = 6; d >= 1; --d) {
-          const double yv = (k - d >= 0) ? cur[k - d] : prev[6 + k - d];
-          s = fma(-r[d - 1], yv, s);
-        }
-        out[k * NT + t] = s * dinv[6 * t + k];
-      }
-      cur[k] = s;
-    }
+    for (int k = 0; k < 6; ++k)
 #pragma unroll
-    for (int k = 0; k < 6; ++k) prev[k] = cur[k];
+      for (int d = 6; d > k; --d) p[k] = fma(-Lr[k][d - 1], prev[6 + k - d], p[k]);
+    // intra-block triangle, outer-product order
+#pragma unroll
+    for (int j = 0; j < 6; ++j)
+#pragma unroll
+      for (int k = j + 1; k < 6; ++k) p[k] = fma(-Lr[k][k - j - 1], p[j], p[k]);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { out[k * NT + t] = p[k] * dv[k]; prev[k] = p[k]; }
   }
-  // backward: L' x = D^-1 y in outer-product form (row i of L updates the 6 rows above it)
+  // backward: L' x = D^-1 y, outer-product order (every finished x_i updates the 6 rows above it)
   double a_cur[6];
-  {
-    const int t = t1 - 1;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) a_cur[k] = (k < blk_nv(t, Nt)) ? out[k * NT + t] : 0.0;
-  }
+  for (int k = 0; k < 6; ++k) a_cur[k] = out[k * NT + t1 - 1];
   for (int t = t1 - 1; t >= t0; --t) {
-    const int nv = blk_nv(t, Nt);
-    double a_prev[6];
+    double Lr[6][6], a_prev[6];
+    load_rows(L6, t, Lr);
+    const int ta = t > t0 ? t - 1 : t0;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) a_prev[k] = (t > t0) ? out[k * NT + t - 1] : 0.0;
+    for (int k = 0; k < 6; ++k) a_prev[k] = out[k * NT + ta];
 #pragma unroll
     for (int k = 5; k >= 0; --k) {
-      if (k < nv) {
-        const double xv = a_cur[k];
-        out[k * NT + t] = xv;
-        const double *r = L6 + (size_t)(6 * t + k) * 6;
+      const double xv = a_cur[k];
+      out[k * NT + t] = xv;
 #pragma unroll
-        for (int d = 1; d <= 6; ++d) {
-          if (k - d >= 0) a_cur[k - d] = fma(-r[d - 1], xv, a_cur[k - d]);
-          else if (t > t0) a_prev[6 + k - d] = fma(-r[d - 1], xv, a_prev[6 + k - d]);
-        }
+      for (int d = 1; d <= 6; ++d) {
+        if (k - d >= 0) a_cur[k - d] = fma(-Lr[k][d - 1], xv, a_cur[k - d]);
+        else a_prev[6 + k - d] = fma(-Lr[k][d - 1], xv, a_prev[6 + k - d]);  // discarded when t == t0
       }
     }
 #pragma unroll
@@ -155,7 +154,7 @@ __device__ __forceinline__ double coupling(const double *L6, int tr, int kr, int
 }
 
 // ---- F2: Schur complement contributions of partition p, streamed ----
-__device__ void schur_partition(const BandMem &bm, const Parts &pt, int p, int Nt) {
+__device__ void schur_partition(const BandMem &bm, const Parts &pt, int p) {
   const double *L6 = bm.L6, *dinv = bm.dinv;
   const int t0 = pt.start(p), t1 = t0 + pt.len(p);
   double *GCC = bm.G + p * 78, *GBB = GCC + 21, *GBC = GBB + 21;
@@ -171,22 +170,19 @@ __device__ void schur_partition(const BandMem &bm, const Parts &pt, int p, int N
 #pragma unroll
       for (int k = 0; k < 6; ++k) prev[a][k] = 0.0;
     for (int t = t0; t < t1; ++t) {
-      const int nv = blk_nv(t, Nt);
 #pragma unroll
       for (int k = 0; k < 6; ++k) {
         const double *r = L6 + (size_t)(6 * t + k) * 6;
-        const double di = (k < nv) ? dinv[6 * t + k] : 0.0;
+        const double di = dinv[6 * t + k];
         double ya[6];
 #pragma unroll
         for (int a = 0; a < 6; ++a) {
           double s = 0.0;
-          if (k < nv) {
-            if (t == t0 && a >= k) s = coupling(L6, t0, k, a);  // C column a, nonzero in the first block only
+          if (t == t0 && a >= k) s = coupling(L6, t0, k, a);  // C column a, nonzero in the first block only
 #pragma unroll
-            for (int d = 6; d >= 1; --d) {
-              const double yv = (k - d >= 0) ? win[a][k - d] : prev[a][6 + k - d];
-              s = fma(-r[d - 1], yv, s);
-            }
+          for (int d = 6; d >= 1; --d) {
+            const double yv = (k - d >= 0) ? win[a][k - d] : prev[a][6 + k - d];
+            s = fma(-r[d - 1], yv, s);
           }
           win[a][k] = s;
           ya[a] = s;
@@ -244,14 +240,19 @@ __device__ void schur_partition(const BandMem &bm, const Parts &pt, int p, int N
   }
 }
 
-// ---- whole factorization, executed by warp 0 (all 32 lanes call it) ----
-__device__ void band_factor_warp(const BandMem &bm, int Nt) {
+// ---- whole factorization, executed by one warp (all 32 lanes call it) ----
+// __noinline__: the factor/solve get their own register allocation instead of competing with the
+// register-resident row state of the caller (saved/restored around the call by the solver warp only)
+template <bool SH>
+__device__ __noinline__ void band_factor_warp(const BandMem bm, int Nt) {
+  if (SH) { __builtin_assume(__isShared(bm.L6)); __builtin_assume(__isShared(bm.dinv)); }
+  __builtin_assume(__isShared(bm.Sinv)); __builtin_assume(__isShared(bm.sv)); __builtin_assume(__isShared(bm.G));
   const Parts pt = make_parts(Nt);
   const int lane = threadIdx.x & 31;
-  if (lane < pt.P) interior_factor(bm.L6, bm.dinv, pt.start(lane), pt.start(lane) + pt.len(lane), Nt);
+  if (lane < pt.P) interior_factor(bm.L6, bm.dinv, pt.start(lane), pt.start(lane) + pt.len(lane));
   __syncwarp();
   if (pt.P == 1) return;
-  if (lane < pt.P) schur_partition(bm, pt, lane, Nt);
+  if (lane < pt.P) schur_partition(bm, pt, lane);
   __syncwarp();
   // F3: assemble S (dense, symmetric) and invert it in place (Gauss-Jordan, SPD: no pivoting)
   const int Ns = 6 * (pt.P - 1);
@@ -292,19 +293,24 @@ __device__ void band_factor_warp(const BandMem &bm, int Nt) {
   }
 }
 
-// ---- solve H x = b: b in `rhs` (SoA, overwritten by x), `tmp` is a scratch vector; warp 0 ----
-__device__ void band_solve_warp(const BandMem &bm, double *rhs, double *tmp, int Nt, int NT) {
+// ---- solve H x = b: b in `rhs` (SoA, overwritten by x), `tmp` is a scratch vector; one warp ----
+template <bool SH>
+__device__ __noinline__ void band_solve_warp(const BandMem bm, double *rhs, double *tmp, int Nt, int NT) {
+  if (SH) { __builtin_assume(__isShared(bm.L6)); __builtin_assume(__isShared(bm.dinv)); }
+  __builtin_assume(__isShared(bm.Sinv)); __builtin_assume(__isShared(bm.sv));
+  __builtin_assume(__isShared(rhs)); __builtin_assume(__isShared(tmp));
   const Parts pt = make_parts(Nt);
   const int lane = threadIdx.x & 31;
-  const double zero6[6] = {0, 0, 0, 0, 0, 0};
   if (pt.P == 1) {
-    if (lane == 0) interior_solve(bm.L6, bm.dinv, rhs, rhs, 0, Nt, Nt, NT, zero6, zero6);
+    if (lane == 0) interior_solve(bm.L6, bm.dinv, rhs, rhs, 0, Nt, NT);
     __syncwarp();
     return;
   }
+  long long dbg_t0 = clock64();
   const int t0 = pt.start(lane < pt.P ? lane : 0), t1 = t0 + pt.len(lane < pt.P ? lane : 0);
-  if (lane < pt.P) interior_solve(bm.L6, bm.dinv, rhs, tmp, t0, t1, Nt, NT, zero6, zero6);  // S1
+  if (lane < pt.P) interior_solve(bm.L6, bm.dinv, rhs, tmp, t0, t1, NT);  // S1
   __syncwarp();
+  DBG_T(0);
   const int Ns = 6 * (pt.P - 1);
   double *g = bm.sv, *xs = bm.sv + kMaxNs;
   for (int e = lane; e < Ns; e += 32) {  // S2: separator right-hand side
@@ -313,46 +319,53 @@ __device__ void band_solve_warp(const BandMem &bm, double *rhs, double *tmp, int
 #pragma unroll
     for (int kc = 0; kc < 6; ++kc)
       if (kc >= k) s = fma(-coupling(bm.L6, T, k, kc), tmp[kc * NT + T - 1], s);
-    const int nvn = blk_nv(T + 1, Nt);
 #pragma unroll
     for (int kr = 0; kr < 6; ++kr)
-      if (kr <= k && kr < nvn) s = fma(-coupling(bm.L6, T + 1, kr, k), tmp[kr * NT + T + 1], s);
+      if (kr <= k) s = fma(-coupling(bm.L6, T + 1, kr, k), tmp[kr * NT + T + 1], s);
     g[e] = s;
   }
   __syncwarp();
+  DBG_T(1);
   for (int r = lane; r < Ns; r += 32) {  // x_sep = Sinv g
-    double s0 = 0.0, s1 = 0.0;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
     const double *Sr = bm.Sinv + r * Ns;
-    int cidx = 0;
-    for (; cidx + 1 < Ns; cidx += 2) { s0 = fma(Sr[cidx], g[cidx], s0); s1 = fma(Sr[cidx + 1], g[cidx + 1], s1); }
-    if (cidx < Ns) s0 = fma(Sr[cidx], g[cidx], s0);
-    xs[r] = s0 + s1;
+#pragma unroll 2
+    for (int cidx = 0; cidx < Ns; cidx += 6) {  // Ns is a multiple of 6
+      s0 = fma(Sr[cidx], g[cidx], s0); s1 = fma(Sr[cidx + 1], g[cidx + 1], s1); s2 = fma(Sr[cidx + 2], g[cidx + 2], s2);
+      s0 = fma(Sr[cidx + 3], g[cidx + 3], s0); s1 = fma(Sr[cidx + 4], g[cidx + 4], s1); s2 = fma(Sr[cidx + 5], g[cidx + 5], s2);
+    }
+    xs[r] = (s0 + s1) + s2;
   }
   __syncwarp();
+  DBG_T(2);
   for (int e = lane; e < Ns; e += 32) rhs[(e % 6) * NT + pt.sep(e / 6)] = xs[e];
   if (lane < pt.P) {  // S3: interiors with the separator solution moved to the right-hand side
-    double af[6] = {0, 0, 0, 0, 0, 0}, al[6] = {0, 0, 0, 0, 0, 0};
     if (lane > 0) {  // rows of the first block couple to the previous separator
       const double *xp = xs + 6 * (lane - 1);
-      const int nv = blk_nv(t0, Nt);
 #pragma unroll
-      for (int k = 0; k < 6; ++k)
-        if (k < nv)
+      for (int k = 0; k < 6; ++k) {
+        double a = rhs[k * NT + t0];
 #pragma unroll
-          for (int kc = 0; kc < 6; ++kc)
-            if (kc >= k) af[k] = fma(-coupling(bm.L6, t0, k, kc), xp[kc], af[k]);
+        for (int kc = 0; kc < 6; ++kc)
+          if (kc >= k) a = fma(-coupling(bm.L6, t0, k, kc), xp[kc], a);
+        rhs[k * NT + t0] = a;
+      }
     }
     if (lane < pt.P - 1) {  // columns of the last block couple to the next separator's rows
       const double *xn = xs + 6 * lane;
 #pragma unroll
-      for (int kc = 0; kc < 6; ++kc)
+      for (int kc = 0; kc < 6; ++kc) {
+        double a = rhs[kc * NT + t1 - 1];
 #pragma unroll
         for (int kr = 0; kr < 6; ++kr)
-          if (kr <= kc) al[kc] = fma(-coupling(bm.L6, t1, kr, kc), xn[kr], al[kc]);
+          if (kr <= kc) a = fma(-coupling(bm.L6, t1, kr, kc), xn[kr], a);
+        rhs[kc * NT + t1 - 1] = a;
+      }
     }
-    interior_solve(bm.L6, bm.dinv, rhs, rhs, t0, t1, Nt, NT, af, al);
+    interior_solve(bm.L6, bm.dinv, rhs, rhs, t0, t1, NT);
   }
   __syncwarp();
+  DBG_T(3);
 }
 
 }  // namespace csdo

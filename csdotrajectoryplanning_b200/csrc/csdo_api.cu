@@ -3,6 +3,7 @@
 // usable sm_100 device every compute entry point returns CSDO_ERR_CUDA.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -23,13 +24,15 @@ struct csdo_handle {
   cudaStream_t stream = nullptr;
   csdo_params P{};
   std::string err;
-  int num_sms = 0, smem_limit = 0;
+  int num_sms = 0, smem_limit = 0, smem_limit_sm = 0;
   DevBuf scratch, queue, step_cnt;
   std::vector<DevBuf> stage;  // staging buffers of the host-pointer entry points
   csdo_launch_info last{};
 };
 
 namespace {
+
+constexpr int PL_BYTES_PER_PLANE = 6 * 4 * 8;
 
 bool set_err(csdo_handle *h, const char *what, cudaError_t e) {
   if (e == cudaSuccess) return false;
@@ -148,18 +151,27 @@ int run_refine(csdo_handle *h, const DevBatch &B, const DevOut &O, int max_nt, i
   const int block = std::max(64, NT);
   Layout LY{};
   int occ = 0;
-  for (int tier = 0; tier <= 2; ++tier) {
+  for (int tier = 0; tier <= 2; tier += 2) {   // 0: band factor in shared memory, 2: in global scratch
     if (tier == 2 && occ > 0) break;
-    const Layout l = make_layout(NT, KMAX, tier);
+    const Layout l = make_layout(NT, KMAX, tier, 0);
     if (l.smem_doubles * 8 + 1024 > h->smem_limit) continue;
     const int o = refine_occupancy(block, l.smem_doubles * 8);
     if (o > occ) { occ = o; LY = l; }
+  }
+  if (occ >= 1) {
+    // spend the shared memory that the chosen residency leaves free on the agents' plane rows
+    // (192 B per plane): agents with K <= KS keep them on chip, the rest use global scratch
+    const int budget = h->smem_limit_sm / occ - 1024 - LY.smem_doubles * 8;
+    int KS = std::min(KMAX, std::max(0, budget / (PL_BYTES_PER_PLANE)));
+    KS &= ~1;
+    Layout l = make_layout(NT, KMAX, LY.tier, KS);
+    if (refine_occupancy(block, l.smem_doubles * 8) >= occ) LY = l;
   }
   if (occ < 1) { h->err = "horizon does not fit the kernel's shared-memory layout"; return CSDO_ERR_UNSUPPORTED; }
   const int grid = std::min(B.n_agents, h->num_sms * occ);
   int rc;
   if ((rc = ensure(h, h->scratch, (size_t)grid * LY.slot_doubles * sizeof(double)))) return rc;
-  if ((rc = ensure(h, h->queue, 64))) return rc;
+  if ((rc = ensure(h, h->queue, 2048))) return rc;
   if (set_err(h, "launch_refine",
               launch_refine(B, O, h->P, LY, static_cast<double *>(h->scratch.p), static_cast<int *>(h->queue.p),
                             grid, block, stream)))
@@ -215,6 +227,7 @@ int csdo_create(const csdo_params *params, int device, csdo_handle **out) {
   if (h->P.osqp_max_iter < 1 || h->P.scaling < 0 || h->P.max_iter < 0) { delete h; return CSDO_ERR_INVALID; }
   h->num_sms = prop.multiProcessorCount;
   h->smem_limit = (int)prop.sharedMemPerBlockOptin;
+  h->smem_limit_sm = (int)prop.sharedMemPerMultiprocessor;
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return CSDO_ERR_CUDA; }
   *out = h;
   return CSDO_OK;
@@ -292,6 +305,18 @@ int csdo_refine(csdo_handle *h, const csdo_batch *in, csdo_result *out) {
   if ((rc = download(h, out->inst_status, O.inst_status, I))) return rc;
   if ((rc = download(h, out->inst_static_legal, O.inst_static_legal, I))) return rc;
   if (set_err(h, "refine", cudaStreamSynchronize(h->stream))) return CSDO_ERR_CUDA;
+  if (getenv("CSDO_PROFILE")) {   // developer aid: per-phase cycles of thread 0, summed over CTAs
+    unsigned long long ph[8];
+    cudaMemcpy(ph, static_cast<char *>(h->queue.p) + 8, sizeof(ph), cudaMemcpyDeviceToHost);
+    static const char *names[8] = {"corridor", "assemble", "ruiz", "factor", "solve", "rows", "check", "other"};
+    double tot = 0;
+    for (int k = 0; k < 8; ++k) tot += (double)ph[k];
+    for (int k = 0; k < 8; ++k)
+      fprintf(stderr, "[csdo profile] %-9s %6.2f%%  %.3e cycles\n", names[k], 100.0 * ph[k] / tot, (double)ph[k]);
+    unsigned long long dbg[16];
+    csdo::read_debug_counters(dbg);
+    fprintf(stderr, "[csdo profile] solve parts: S1 %.3e  S2 %.3e  Sinv %.3e  S3 %.3e\n", (double)dbg[0], (double)dbg[1], (double)dbg[2], (double)dbg[3]);
+  }
   return CSDO_OK;
 }
 

@@ -29,7 +29,7 @@ enum Ro : int {
   RO_SN = 0, RO_CS, RO_A1, RO_A2, RO_A3, RO_B3, RO_KR0, RO_KR1, RO_KR2,
   RO_CL0, RO_CL1, RO_CL2, RO_CL3, RO_CU0, RO_CU1, RO_CU2, RO_CU3, RO_TRX, RO_TRY, RO_COUNT
 };
-// per plane-row arrays (stride KP = 4*KMAX)
+// per plane-row record (AoS, 6 doubles = 3 LDS.128): pl[row * 6 + field]
 enum Pl : int { PL_A = 0, PL_B, PL_G, PL_U, PL_E, PL_W, PL_COUNT };
 // local unknown indices inside visit_rows: own step 0..5, next step x,y,yaw,steer 6..9
 enum Var : int { VX = 0, VY, VP, VS, VV, VW, NX, NY, NP, NS };
@@ -43,15 +43,21 @@ struct BandMem {
 
 struct Ctx {
   int Nt, NT, K, KP, No, tid, nthr, t;  // t = this thread's time step (tid), valid if tid < Nt
-  bool active, has_next;
+  bool active, has_next, l_shared;
+  int solver_warp;  // the warp of this CTA that runs the band factor/solve
   // shared-memory vectors, SoA with stride NT: v[k*NT + t]
-  double *x, *xt, *rhs, *D, *carry, *w, *E, *red;
-  double *cfgw, *cfgE;  // 6 start/goal rows (contiguous after w / E)
-  int *pstart;          // [Nt+1] first plane of each step
-  BandMem bm;           // band factor storage (band_solver.cuh)
-  double *ro;           // RO_COUNT planes, generic pointer
+  double *x, *xt, *rhs, *D, *carry, *red;
+  int *pstart;  // [Nt+1] first plane of each step
+  double *ros;  // read-only per-step row data, RO_COUNT planes (shared)
+  double *cfgs; // 6 start/goal pins (shared)
+  double *Es;   // Ruiz row scaling of the fixed rows, 16 planes (shared; read-only during the ADMM loop)
+  double *ws;   // ADMM row state w = z_hat + y/rho of the fixed rows, 16 planes (shared)
+  BandMem bm;   // band factor storage (band_solver.cuh)
   // per-CTA global scratch
-  double *cur, *sol, *dy, *pl;
+  double *cur, *sol, *dy;
+  double *pl;       // plane rows of this agent: shared memory when they fit (K <= KS), else global scratch
+  double *pl_smem, *pl_glob;
+  int KS;
   // batch views of this agent
   const double *guess;      // 6 planes, stride Nt
   const double *plane_abc;  // [K][12]
@@ -59,8 +65,8 @@ struct Ctx {
   const double *obs;        // [No][3]
   double *corr;             // 8 planes, stride Nt (output array doubles as the live corridor)
   double dimx, dimy;
-  double cfg[6];
   double rho, c;  // current rho and Ruiz cost scaling
+  long long ph[8];  // phase cycle counters (thread 0 is the one reported)
 };
 
 __device__ __forceinline__ double limit_scaling(double v) {
@@ -98,54 +104,67 @@ __device__ __forceinline__ void block_reduce(double (&v)[N], double *red) {
 }
 
 // ---- the rows of time step t (reference sqp/dsqp_solver.cc:646-1129) ----
-// f.row<NC>(i0,c0,i1,c1,i2,c2,i3,c3, l, u, w, E): NC coefficients on local
-// unknowns i*, raw bounds l,u, the row's ADMM state w and Ruiz factor E.
+// f.row<NC>(rid, i0,c0,i1,c1,i2,c2,i3,c3, l, u, w, E): row id (0..15 fixed rows, -1 plane rows),
+// NC coefficients on local unknowns i*, raw bounds l,u, the row's ADMM state w and Ruiz factor E.
 template <class F>
-__device__ __forceinline__ void visit_rows(const Ctx &c, const csdo_params &P, F &f) {
-  const int NT = c.NT, t = c.t;
-  const double sn = c.ro[RO_SN * NT + t], cs = c.ro[RO_CS * NT + t];
+__device__ __forceinline__ void visit_rows(Ctx &c, const csdo_params &P, F &f) {
+  const int t = c.t;
+  __builtin_assume(__isShared(c.ros));
+  __builtin_assume(__isShared(c.cfgs));
+  __builtin_assume(__isShared(c.Es));
+  __builtin_assume(__isShared(c.ws));
+  __builtin_assume(__isShared(c.pstart));
+  const double *ro_ = c.ros + t;
+  const int NTs = c.NT;
+#define RO(i) ro_[(i) * NTs]
+  const double sn = RO(RO_SN), cs = RO(RO_CS);
   if (c.has_next) {
     // calcKineConstraint :646-744, lb = ub = -C
-    const double kr0 = c.ro[RO_KR0 * NT + t], kr1 = c.ro[RO_KR1 * NT + t], kr2 = c.ro[RO_KR2 * NT + t];
-    f.template row<4>(VX, 1.0, VP, c.ro[RO_A1 * NT + t], VV, P.dt * cs, NX, -1.0, kr0, kr0, c.w[0 * NT + t], c.E[0 * NT + t]);
-    f.template row<4>(VY, 1.0, VP, c.ro[RO_A2 * NT + t], VV, P.dt * sn, NY, -1.0, kr1, kr1, c.w[1 * NT + t], c.E[1 * NT + t]);
-    f.template row<4>(VP, 1.0, VS, c.ro[RO_A3 * NT + t], VV, c.ro[RO_B3 * NT + t], NP, -1.0, kr2, kr2, c.w[2 * NT + t], c.E[2 * NT + t]);
-    f.template row<3>(VS, 1.0, VW, P.dt * 1.0, NS, -1.0, 0, 0.0, -0.0, -0.0, c.w[3 * NT + t], c.E[3 * NT + t]);
+    f.template row<4>(0, VX, 1.0, VP, RO(RO_A1), VV, P.dt * cs, NX, -1.0, RO(RO_KR0), RO(RO_KR0), c.ws[0 * c.NT + t], c.Es[0 * c.NT + t]);
+    f.template row<4>(1, VY, 1.0, VP, RO(RO_A2), VV, P.dt * sn, NY, -1.0, RO(RO_KR1), RO(RO_KR1), c.ws[1 * c.NT + t], c.Es[1 * c.NT + t]);
+    f.template row<4>(2, VP, 1.0, VS, RO(RO_A3), VV, RO(RO_B3), NP, -1.0, RO(RO_KR2), RO(RO_KR2), c.ws[2 * c.NT + t], c.Es[2 * c.NT + t]);
+    f.template row<3>(3, VS, 1.0, VW, P.dt * 1.0, NS, -1.0, 0, 0.0, -0.0, -0.0, c.ws[3 * c.NT + t], c.Es[3 * c.NT + t]);
   }
-  // calcCfgConstraint :746-788 (cfg = x0,xN,y0,yN,yaw0,yawN)
+  // calcCfgConstraint :746-788 (cfg = x0,xN,y0,yN,yaw0,yawN); rows 13..15 of the first/last step
   if (t == 0) {
-    f.template row<1>(VX, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, c.cfg[0], c.cfg[0], c.cfgw[0], c.cfgE[0]);
-    f.template row<1>(VY, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, c.cfg[2], c.cfg[2], c.cfgw[2], c.cfgE[2]);
-    f.template row<1>(VP, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, c.cfg[4], c.cfg[4], c.cfgw[4], c.cfgE[4]);
+    f.template row<1>(13, VX, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, c.cfgs[0], c.cfgs[0], c.ws[13 * c.NT + t], c.Es[13 * c.NT + t]);
+    f.template row<1>(14, VY, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, c.cfgs[2], c.cfgs[2], c.ws[14 * c.NT + t], c.Es[14 * c.NT + t]);
+    f.template row<1>(15, VP, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, c.cfgs[4], c.cfgs[4], c.ws[15 * c.NT + t], c.Es[15 * c.NT + t]);
   }
   if (t == c.Nt - 1) {
-    f.template row<1>(VX, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, c.cfg[1], c.cfg[1], c.cfgw[1], c.cfgE[1]);
-    f.template row<1>(VY, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, c.cfg[3], c.cfg[3], c.cfgw[3], c.cfgE[3]);
-    f.template row<1>(VP, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, c.cfg[5], c.cfg[5], c.cfgw[5], c.cfgE[5]);
+    f.template row<1>(13, VX, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, c.cfgs[1], c.cfgs[1], c.ws[13 * c.NT + t], c.Es[13 * c.NT + t]);
+    f.template row<1>(14, VY, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, c.cfgs[3], c.cfgs[3], c.ws[14 * c.NT + t], c.Es[14 * c.NT + t]);
+    f.template row<1>(15, VP, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, c.cfgs[5], c.cfgs[5], c.ws[15 * c.NT + t], c.Es[15 * c.NT + t]);
   }
   // calcCorridorConstraint :874-968: D = [I,0,-f2x sin; 0,I,f2x cos; I,0,-r2x sin; 0,I,r2x cos]
-  f.template row<2>(VX, 1.0, VP, -P.f2x * sn, 0, 0.0, 0, 0.0, c.ro[RO_CL0 * NT + t], c.ro[RO_CU0 * NT + t], c.w[4 * NT + t], c.E[4 * NT + t]);
-  f.template row<2>(VY, 1.0, VP, P.f2x * cs, 0, 0.0, 0, 0.0, c.ro[RO_CL1 * NT + t], c.ro[RO_CU1 * NT + t], c.w[5 * NT + t], c.E[5 * NT + t]);
-  f.template row<2>(VX, 1.0, VP, -P.r2x * sn, 0, 0.0, 0, 0.0, c.ro[RO_CL2 * NT + t], c.ro[RO_CU2 * NT + t], c.w[6 * NT + t], c.E[6 * NT + t]);
-  f.template row<2>(VY, 1.0, VP, P.r2x * cs, 0, 0.0, 0, 0.0, c.ro[RO_CL3 * NT + t], c.ro[RO_CU3 * NT + t], c.w[7 * NT + t], c.E[7 * NT + t]);
+  f.template row<2>(4, VX, 1.0, VP, -P.f2x * sn, 0, 0.0, 0, 0.0, RO(RO_CL0), RO(RO_CU0), c.ws[4 * c.NT + t], c.Es[4 * c.NT + t]);
+  f.template row<2>(5, VY, 1.0, VP, P.f2x * cs, 0, 0.0, 0, 0.0, RO(RO_CL1), RO(RO_CU1), c.ws[5 * c.NT + t], c.Es[5 * c.NT + t]);
+  f.template row<2>(6, VX, 1.0, VP, -P.r2x * sn, 0, 0.0, 0, 0.0, RO(RO_CL2), RO(RO_CU2), c.ws[6 * c.NT + t], c.Es[6 * c.NT + t]);
+  f.template row<2>(7, VY, 1.0, VP, P.r2x * cs, 0, 0.0, 0, 0.0, RO(RO_CL3), RO(RO_CU3), c.ws[7 * c.NT + t], c.Es[7 * c.NT + t]);
   // calcTrustRegionConstraint :970-994 (centre = initial guess, all SQP iterations)
-  {
-    const double trx = c.ro[RO_TRX * NT + t], try_ = c.ro[RO_TRY * NT + t];
-    f.template row<1>(VX, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, -P.r_trust + trx, P.r_trust + trx, c.w[8 * NT + t], c.E[8 * NT + t]);
-    f.template row<1>(VY, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, -P.r_trust + try_, P.r_trust + try_, c.w[9 * NT + t], c.E[9 * NT + t]);
-  }
+  f.template row<1>(8, VX, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, -P.r_trust + RO(RO_TRX), P.r_trust + RO(RO_TRX), c.ws[8 * c.NT + t], c.Es[8 * c.NT + t]);
+  f.template row<1>(9, VY, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, -P.r_trust + RO(RO_TRY), P.r_trust + RO(RO_TRY), c.ws[9 * c.NT + t], c.Es[9 * c.NT + t]);
   // calcMaxCtrlAndSteerConstraint :996-1039
   if (c.has_next) {
-    f.template row<1>(VV, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, -P.max_v, P.max_v, c.w[10 * NT + t], c.E[10 * NT + t]);
-    f.template row<1>(VW, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, -P.max_omega, P.max_omega, c.w[11 * NT + t], c.E[11 * NT + t]);
+    f.template row<1>(10, VV, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, -P.max_v, P.max_v, c.ws[10 * c.NT + t], c.Es[10 * c.NT + t]);
+    f.template row<1>(11, VW, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, -P.max_omega, P.max_omega, c.ws[11 * c.NT + t], c.Es[11 * c.NT + t]);
   }
-  f.template row<1>(VS, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, -P.steer_max, P.steer_max, c.w[12 * NT + t], c.E[12 * NT + t]);
+  f.template row<1>(12, VS, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, -P.steer_max, P.steer_max, c.ws[12 * c.NT + t], c.Es[12 * c.NT + t]);
   // calcInterVehicleConstraint :1097-1129: 4 rows per plane of this step, l = -inf
   const int k0 = c.pstart[t], k1 = c.pstart[t + 1];
-  for (int r = 4 * k0; r < 4 * k1; ++r) {
-    f.template row<3>(VX, c.pl[PL_A * c.KP + r], VY, c.pl[PL_B * c.KP + r], VP, c.pl[PL_G * c.KP + r], 0, 0.0,
-                      -INFINITY, c.pl[PL_U * c.KP + r], c.pl[PL_W * c.KP + r], c.pl[PL_E * c.KP + r]);
+  if (c.pl == c.pl_smem) {  // on-chip plane rows: plain shared-memory loads (LDS), not generic ones
+    __builtin_assume(__isShared(c.pl_smem));
+    for (int r = 4 * k0; r < 4 * k1; ++r) {
+      double *q = c.pl_smem + (size_t)PL_COUNT * r;
+      f.template row<3>(-1, VX, q[PL_A], VY, q[PL_B], VP, q[PL_G], 0, 0.0, -INFINITY, q[PL_U], q[PL_W], q[PL_E]);
+    }
+  } else {
+    for (int r = 4 * k0; r < 4 * k1; ++r) {
+      double *q = c.pl_glob + (size_t)PL_COUNT * r;
+      f.template row<3>(-1, VX, q[PL_A], VY, q[PL_B], VP, q[PL_G], 0, 0.0, -INFINITY, q[PL_U], q[PL_W], q[PL_E]);
+    }
   }
+#undef RO
 }
 
 // rho of a row from its scaled bounds (OSQP set_rho_vec; "loose" rows cannot occur)

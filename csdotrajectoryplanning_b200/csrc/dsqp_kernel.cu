@@ -193,10 +193,10 @@ struct StepF {
   double acc[10];
   double alpha, rho, rho_old;
   bool store_dy;
-  double *dy_base;       // shared-row delta_y (only kept when the agent has no planes)
-  const double *w_base;  // base of the shared w block
+  double *dy_base;  // delta_y of this thread's fixed rows (only kept when the agent has no planes)
+  int dy_stride;
   template <int NC>
-  __device__ __forceinline__ void row(int i0, double c0, int i1, double c1, int i2, double c2, int i3,
+  __device__ __forceinline__ void row(int rid, int i0, double c0, int i1, double c1, int i2, double c2, int i3,
                                       double c3, double l, double u, double &w, double &E) {
     const double e = E;
     const double ls = e * l, us = e * u;
@@ -218,7 +218,7 @@ struct StepF {
       const double zhat = alpha * zt + (1.0 - alpha) * zo;
       wn = zhat + yor;
       zn = clipd(wn, ls, us);
-      if (store_dy) dy_base[&w - w_base] = rho_i * (zhat - zn);
+      if (store_dy && rid >= 0) dy_base[rid * dy_stride] = rho_i * (zhat - zn);
     }
     w = wn;
     const double g = e * (rho_i * (2.0 * zn - wn));  // E (rho z - y)
@@ -242,9 +242,9 @@ struct CheckF {
   double rho;
   bool with_dy;
   const double *dy_base;
-  const double *w_base;
+  int dy_stride;
   template <int NC>
-  __device__ __forceinline__ void row(int i0, double c0, int i1, double c1, int i2, double c2, int i3,
+  __device__ __forceinline__ void row(int rid, int i0, double c0, int i1, double c1, int i2, double c2, int i3,
                                       double c3, double l, double u, double &w, double &E) {
     const double e = E, einv = 1.0 / e;
     const double ls = e * l, us = e * u;
@@ -261,7 +261,7 @@ struct CheckF {
     nrm[N_AX_U] = fmax(nrm[N_AX_U], fabs(einv * ax));
     row_scatter<NC>(acc, e * y, i0, c0, i1, c1, i2, c2, i3, c3);
     if (with_dy) {
-      const double dy = dy_base[&w - w_base];
+      const double dy = rid >= 0 ? dy_base[rid * dy_stride] : 0.0;
       nrm[N_DY] = fmax(nrm[N_DY], fabs(e * dy));
       ineq_lhs += us * (dy > 0 ? dy : 0) + ls * (dy < 0 ? dy : 0);
       row_scatter<NC>(accd, e * dy, i0, c0, i1, c1, i2, c2, i3, c3);
@@ -274,7 +274,7 @@ struct ScaleF {
   double dv[10];    // current D of the touched unknowns
   double cmax[10];  // max_i E_i |a_ij| per touched unknown (without D_j)
   template <int NC>
-  __device__ __forceinline__ void row(int i0, double c0, int i1, double c1, int i2, double c2, int i3,
+  __device__ __forceinline__ void row(int rid, int i0, double c0, int i1, double c1, int i2, double c2, int i3,
                                       double c3, double l, double u, double &w, double &E) {
     const double e = E;
     double rn = fabs(c0) * dv[i0];
@@ -290,7 +290,7 @@ struct ScaleF {
 // reset E to 1 before scaling
 struct ResetF {
   template <int NC>
-  __device__ __forceinline__ void row(int, double, int, double, int, double, int, double, double, double,
+  __device__ __forceinline__ void row(int, int, double, int, double, int, double, int, double, double, double,
                                       double &w, double &E) {
     E = 1.0;
     w = 0.0;
@@ -311,7 +311,7 @@ struct HasmF {
     else nd[i - 6] += v;  // only i == j occurs
   }
   template <int NC>
-  __device__ __forceinline__ void row(int i0, double c0, int i1, double c1, int i2, double c2, int i3,
+  __device__ __forceinline__ void row(int rid, int i0, double c0, int i1, double c1, int i2, double c2, int i3,
                                       double c3, double l, double u, double &w, double &E) {
     const double e = E;
     const double h = row_rho(e * l, e * u, rho) * (e * e);
@@ -337,30 +337,30 @@ __device__ __forceinline__ void load_xv(const Ctx &c, const double *v, double (&
 __device__ __forceinline__ int nvar(const Ctx &c) { return c.has_next ? 6 : 4; }
 
 // linearization-dependent per-step data (dsqp_solver.cc:670-718, 893-948, 1116-1123)
-__device__ void assemble_rows(Ctx &c, const csdo_params &P) {
+__device__ __forceinline__ void assemble_rows(Ctx &c, const csdo_params &P) {
   const int NT = c.NT, Nt = c.Nt, t = c.t;
   if (c.active) {
     const double yaw0 = c.cur[2 * NT + t], st0 = c.cur[3 * NT + t], v0 = c.cur[4 * NT + t];
     const double sn = sin(yaw0), cs = cos(yaw0);
-    c.ro[RO_SN * NT + t] = sn;
-    c.ro[RO_CS * NT + t] = cs;
+    c.ros[RO_SN * NT + c.t] = sn;
+    c.ros[RO_CS * NT + c.t] = cs;
     if (c.has_next) {
       const double cd = cos(st0);
-      c.ro[RO_A1 * NT + t] = -P.dt * (v0 * sn);
-      c.ro[RO_A2 * NT + t] = P.dt * (v0 * cs);
-      c.ro[RO_A3 * NT + t] = (P.dt / P.WB * v0) / (cd * cd);
-      c.ro[RO_B3 * NT + t] = P.dt / P.WB * tan(st0);
-      c.ro[RO_KR0 * NT + t] = -(P.dt * yaw0 * v0 * sn);
-      c.ro[RO_KR1 * NT + t] = -(-P.dt * yaw0 * v0 * cs);
-      c.ro[RO_KR2 * NT + t] = -(-P.dt * (st0 * v0 / P.WB / (cd * cd)));
+      c.ros[RO_A1 * NT + c.t] = -P.dt * (v0 * sn);
+      c.ros[RO_A2 * NT + c.t] = P.dt * (v0 * cs);
+      c.ros[RO_A3 * NT + c.t] = (P.dt / P.WB * v0) / (cd * cd);
+      c.ros[RO_B3 * NT + c.t] = P.dt / P.WB * tan(st0);
+      c.ros[RO_KR0 * NT + c.t] = -(P.dt * yaw0 * v0 * sn);
+      c.ros[RO_KR1 * NT + c.t] = -(-P.dt * yaw0 * v0 * cs);
+      c.ros[RO_KR2 * NT + c.t] = -(-P.dt * (st0 * v0 / P.WB / (cd * cd)));
     }
     const double dxf = -P.f2x * sn, dyf = P.f2x * cs, dxr = -P.r2x * sn, dyr = P.r2x * cs;
     const double exf = P.f2x * (cs + yaw0 * sn), eyf = P.f2x * (sn - yaw0 * cs);
     const double exr = P.r2x * (cs + yaw0 * sn), eyr = P.r2x * (sn - yaw0 * cs);
-    c.ro[RO_CL0 * NT + t] = c.corr[0 * Nt + t] - exf; c.ro[RO_CU0 * NT + t] = c.corr[1 * Nt + t] - exf;
-    c.ro[RO_CL1 * NT + t] = c.corr[2 * Nt + t] - eyf; c.ro[RO_CU1 * NT + t] = c.corr[3 * Nt + t] - eyf;
-    c.ro[RO_CL2 * NT + t] = c.corr[4 * Nt + t] - exr; c.ro[RO_CU2 * NT + t] = c.corr[5 * Nt + t] - exr;
-    c.ro[RO_CL3 * NT + t] = c.corr[6 * Nt + t] - eyr; c.ro[RO_CU3 * NT + t] = c.corr[7 * Nt + t] - eyr;
+    c.ros[RO_CL0 * NT + c.t] = c.corr[0 * Nt + t] - exf; c.ros[RO_CU0 * NT + c.t] = c.corr[1 * Nt + t] - exf;
+    c.ros[RO_CL1 * NT + c.t] = c.corr[2 * Nt + t] - eyf; c.ros[RO_CU1 * NT + c.t] = c.corr[3 * Nt + t] - eyf;
+    c.ros[RO_CL2 * NT + c.t] = c.corr[4 * Nt + t] - exr; c.ros[RO_CU2 * NT + c.t] = c.corr[5 * Nt + t] - exr;
+    c.ros[RO_CL3 * NT + c.t] = c.corr[6 * Nt + t] - eyr; c.ros[RO_CU3 * NT + c.t] = c.corr[7 * Nt + t] - eyr;
     for (int k = c.pstart[t]; k < c.pstart[t + 1]; ++k) {
       const double *pl = c.plane_abc + (size_t)12 * k;
 #pragma unroll
@@ -368,10 +368,11 @@ __device__ void assemble_rows(Ctx &c, const csdo_params &P) {
         const double a = pl[3 * r], b = pl[3 * r + 1], cc = pl[3 * r + 2];
         const double dx = r < 2 ? dxf : dxr, dy = r < 2 ? dyf : dyr;
         const double ex = r < 2 ? exf : exr, ey = r < 2 ? eyf : eyr;
-        c.pl[PL_A * c.KP + 4 * k + r] = a * 1.0;
-        c.pl[PL_B * c.KP + 4 * k + r] = b * 1.0;
-        c.pl[PL_G * c.KP + 4 * k + r] = a * dx + b * dy;
-        c.pl[PL_U * c.KP + 4 * k + r] = -(cc + (a * ex + b * ey));
+        double *q = c.pl + (size_t)PL_COUNT * (4 * k + r);
+        q[PL_A] = a * 1.0;
+        q[PL_B] = b * 1.0;
+        q[PL_G] = a * dx + b * dy;
+        q[PL_U] = -(cc + (a * ex + b * ey));
       }
     }
   }
@@ -379,7 +380,7 @@ __device__ void assemble_rows(Ctx &c, const csdo_params &P) {
 }
 
 // OSQP scale_data, `scaling` Ruiz passes; leaves D, E, c
-__device__ void ruiz_scale(Ctx &c, const csdo_params &P) {
+__device__ __forceinline__ void ruiz_scale(Ctx &c, const csdo_params &P) {
   const int NT = c.NT, t = c.t, Nt = c.Nt;
   if (c.active) {
     ResetF rf;
@@ -454,7 +455,7 @@ __device__ void ruiz_scale(Ctx &c, const csdo_params &P) {
 
 // reduced KKT  H = c D P D + sigma I + D A_raw' diag(rho E^2) A_raw D  into the
 // band storage, then LDL'.
-__device__ void form_and_factor(Ctx &c, const csdo_params &P) {
+__device__ __forceinline__ void form_and_factor(Ctx &c, const csdo_params &P) {
   const int NT = c.NT, t = c.t, Nt = c.Nt;
   HasmF hf;
   if (c.active) {
@@ -472,12 +473,12 @@ __device__ void form_and_factor(Ctx &c, const csdo_params &P) {
     visit_rows(c, P, hf);
 #pragma unroll
     for (int k = 0; k < 4; ++k) c.carry[k * NT + t] = hf.nd[k];
-    // clear this step's band rows
-    const int nv = nvar(c);
-    for (int k = 0; k < nv; ++k) {
+    // clear this step's band rows; the last step's missing v, w are dummy unknowns (H_ii = 1)
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
 #pragma unroll
       for (int d = 0; d < 6; ++d) c.bm.L6[(size_t)(6 * t + k) * 6 + d] = 0.0;
-      c.bm.dinv[6 * t + k] = 0.0;
+      c.bm.dinv[6 * t + k] = 1.0;
     }
   }
   __syncthreads();
@@ -510,9 +511,15 @@ __device__ void form_and_factor(Ctx &c, const csdo_params &P) {
     }
   }
   __syncthreads();
-  if (c.tid < 32) band_factor_warp(c.bm, Nt);
+  if ((c.tid >> 5) == c.solver_warp) {
+    if (c.l_shared) band_factor_warp<true>(c.bm, Nt); else band_factor_warp<false>(c.bm, Nt);
+  }
   __syncthreads();
 }
+
+// optional phase timing (thread 0's clock), accumulated per CTA and added to queue[2..] at exit
+#define PH_T0() long long ph_t0 = clock64()
+#define PH_ADD(id) do { const long long ph_t1 = clock64(); c.ph[id] += ph_t1 - ph_t0; ph_t0 = ph_t1; } while (0)
 
 struct QpOut {
   int status, iters, n_factor;
@@ -525,7 +532,7 @@ __device__ __forceinline__ void finish_rhs(const Ctx &c, const csdo_params &P, c
     const int nv = nvar(c);
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
-      if (k >= nv) continue;
+      if (k >= nv) { c.rhs[k * NT + t] = 0.0; continue; }  // dummy unknowns stay 0
       double a = acc[k];
       if (k < 4 && t > 0) a += c.carry[k * NT + t - 1];
       c.rhs[k * NT + t] = P.sigma * c.x[k * NT + t] + c.D[k * NT + t] * a;
@@ -534,14 +541,14 @@ __device__ __forceinline__ void finish_rhs(const Ctx &c, const csdo_params &P, c
 }
 
 template <int MODE>
-__device__ void step_rows(Ctx &c, const csdo_params &P, bool store_dy, double rho_old) {
+__device__ __forceinline__ void step_rows(Ctx &c, const csdo_params &P, bool store_dy, double rho_old) {
   StepF<MODE> sf;
   if (c.active) {
     load_xv(c, c.xt, sf.xv);
 #pragma unroll
     for (int k = 0; k < 10; ++k) sf.acc[k] = 0.0;
     sf.alpha = P.alpha; sf.rho = c.rho; sf.rho_old = rho_old;
-    sf.store_dy = store_dy; sf.dy_base = c.dy; sf.w_base = c.w;
+    sf.store_dy = store_dy; sf.dy_base = c.dy + c.t; sf.dy_stride = c.NT;
     visit_rows(c, P, sf);
 #pragma unroll
     for (int k = 0; k < 4; ++k) c.carry[k * c.NT + c.t] = sf.acc[6 + k];
@@ -557,7 +564,7 @@ struct CheckOut {
   double ineq_lhs;
 };
 
-__device__ void check_rows(Ctx &c, const csdo_params &P, bool with_dy, CheckOut &co) {
+__device__ __forceinline__ void check_rows(Ctx &c, const csdo_params &P, bool with_dy, CheckOut &co) {
   const int NT = c.NT, t = c.t, Nt = c.Nt;
   // xt <- D x (the current iterate, not x~)
   if (c.active) {
@@ -573,7 +580,7 @@ __device__ void check_rows(Ctx &c, const csdo_params &P, bool with_dy, CheckOut 
     load_xv(c, c.xt, cf.xv);
 #pragma unroll
     for (int k = 0; k < 10; ++k) { cf.acc[k] = 0.0; cf.accd[k] = 0.0; }
-    cf.rho = c.rho; cf.with_dy = with_dy; cf.dy_base = c.dy; cf.w_base = c.w;
+    cf.rho = c.rho; cf.with_dy = with_dy; cf.dy_base = c.dy + c.t; cf.dy_stride = c.NT;
     visit_rows(c, P, cf);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -644,12 +651,15 @@ __device__ int termination_status(const Ctx &c, const csdo_params &P, const Chec
 }
 
 // solveOSQP (dsqp_solver.cc:423-555): setup + warm start + ADMM; solution in c.sol
-__device__ QpOut solve_qp(Ctx &c, const csdo_params &P) {
+__device__ __forceinline__ QpOut solve_qp(Ctx &c, const csdo_params &P) {
   const int NT = c.NT, t = c.t, Nt = c.Nt;
   QpOut out{CSDO_QP_UNSOLVED, 0, 1};
+  PH_T0();
   ruiz_scale(c, P);
+  PH_ADD(2);
   c.rho = fmin(fmax(P.rho, kRhoMin), kRhoMax);
   form_and_factor(c, P);
+  PH_ADD(3);
   // osqp_warm_start_x: x <- Dinv x0, z <- A x, y = 0
   if (c.active) {
 #pragma unroll
@@ -666,9 +676,14 @@ __device__ QpOut solve_qp(Ctx &c, const csdo_params &P) {
   CheckOut co;
   bool checked = false;
   int iter = 0;
+  PH_ADD(5);
   for (iter = 1; iter <= P.osqp_max_iter; ++iter) {
-    if (c.tid < 32) band_solve_warp(c.bm, c.rhs, c.xt, Nt, NT);
+    if ((c.tid >> 5) == c.solver_warp) {
+      if (c.l_shared) band_solve_warp<true>(c.bm, c.rhs, c.xt, Nt, NT);
+      else band_solve_warp<false>(c.bm, c.rhs, c.xt, Nt, NT);
+    }
     __syncthreads();
+    PH_ADD(4);
     if (c.active) {
       const int nv = nvar(c);
 #pragma unroll
@@ -684,6 +699,7 @@ __device__ QpOut solve_qp(Ctx &c, const csdo_params &P) {
     const bool store_dy = keep_dy && (can_check || iter == P.osqp_max_iter);
     if (iter == 1) step_rows<1>(c, P, store_dy, 0.0);
     else step_rows<2>(c, P, store_dy, 0.0);
+    PH_ADD(5);
     checked = false;
     const bool adapt = P.adaptive_rho && P.adaptive_rho_interval && (iter % P.adaptive_rho_interval == 0);
     if (can_check || adapt) {
@@ -694,6 +710,7 @@ __device__ QpOut solve_qp(Ctx &c, const csdo_params &P) {
         for (int k = 0; k < 6; ++k) keep[k] = c.rhs[k * NT + t];
       __syncthreads();
       check_rows(c, P, keep_dy && store_dy, co);
+      PH_ADD(6);
       if (c.active)
 #pragma unroll
         for (int k = 0; k < 6; ++k) c.rhs[k * NT + t] = keep[k];
@@ -715,7 +732,9 @@ __device__ QpOut solve_qp(Ctx &c, const csdo_params &P) {
           c.rho = rho_new;
           out.n_factor++;
           form_and_factor(c, P);
+          PH_ADD(3);
           step_rows<3>(c, P, false, rho_old);
+          PH_ADD(5);
         }
       }
     }
@@ -760,7 +779,7 @@ __device__ QpOut solve_qp(Ctx &c, const csdo_params &P) {
 }
 
 // isFeasible (dsqp_solver.cc:292-420), fully_check = false, on c.sol
-__device__ bool is_feasible(Ctx &c, const csdo_params &P) {
+__device__ __forceinline__ bool is_feasible(Ctx &c, const csdo_params &P) {
   const int NT = c.NT, t = c.t, Nt = c.Nt;
   double s[1] = {0.0};
   double mx[2] = {0.0, 0.0};
@@ -800,9 +819,10 @@ __device__ bool is_feasible(Ctx &c, const csdo_params &P) {
 // ===================================================================
 // the kernel
 // ===================================================================
-__global__ void __launch_bounds__(kMaxThreads, 1)
-dsqp_refine_kernel(const DevBatch B, const DevOut O, const csdo_params P, const Layout LY, double *scratch,
-                   int *queue) {
+// Register budget follows the block size (one thread per time step): horizons <= 128 run with up to
+// 255 registers (2 CTAs/SM), <= 256 with 255 (1 CTA/SM), longer ones with 128.
+__device__ __forceinline__ void refine_body(const DevBatch &B, const DevOut &O, const csdo_params &P,
+                                            const Layout &LY, double *scratch, int *queue) {
   extern __shared__ double smem[];
   __shared__ int s_agent;
   __shared__ int s_flag;
@@ -811,23 +831,36 @@ dsqp_refine_kernel(const DevBatch B, const DevOut O, const csdo_params P, const 
   const int NT = c.NT;
   double *slot = scratch + (size_t)blockIdx.x * LY.slot_doubles;
   c.x = smem + LY.o_x; c.xt = smem + LY.o_xt; c.rhs = smem + LY.o_rhs; c.D = smem + LY.o_D;
-  c.carry = smem + LY.o_carry; c.w = smem + LY.o_w; c.cfgw = c.w + 13 * NT;
-  c.E = smem + LY.o_E; c.cfgE = c.E + 13 * NT; c.red = smem + LY.o_red;
+  c.carry = smem + LY.o_carry; c.red = smem + LY.o_red;
+  c.ros = smem + LY.o_ro; c.cfgs = c.ros + RO_COUNT * NT; c.Es = smem + LY.o_E; c.ws = smem + LY.o_w;
   c.pstart = reinterpret_cast<int *>(smem + LY.o_pstart);
   c.bm.L6 = LY.tier >= 2 ? slot + LY.g_L : smem + LY.o_L;
   c.bm.dinv = c.bm.L6 + 36 * NT;
+  c.l_shared = LY.tier < 2;
   c.bm.Sinv = smem + LY.o_sinv;
   c.bm.sv = c.bm.Sinv + kMaxNs * kMaxNs;
   c.bm.G = c.xt;  // xt and rhs are contiguous and free while a factorization runs
-  c.ro = LY.tier >= 1 ? slot + LY.g_ro : smem + LY.o_ro;
-  c.cur = slot + LY.g_cur; c.sol = slot + LY.g_sol; c.dy = slot + LY.g_dy; c.pl = slot + LY.g_pl;
+  c.cur = slot + LY.g_cur; c.sol = slot + LY.g_sol; c.dy = slot + LY.g_dy;
+  c.pl_glob = slot + LY.g_pl; c.pl_smem = smem + LY.o_pl; c.KS = LY.KS;
 
+  for (int k = 0; k < 8; ++k) c.ph[k] = 0;
+  // The warp that runs the band factor/solve differs between the CTAs resident on one SM, so that
+  // their (single-warp, issue-bound) solves land on different SM sub-partitions (warp id % 4).
+  if (threadIdx.x == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    s_flag = atomicAdd(queue + 32 + (smid & 255), 1);
+  }
+  __syncthreads();
+  c.solver_warp = s_flag % ((blockDim.x + 31) >> 5);
+  __syncthreads();
   for (;;) {
     if (threadIdx.x == 0) s_agent = atomicAdd(queue, 1);
     __syncthreads();
     const int qi = s_agent;
     __syncthreads();
     if (qi >= B.n_agents) break;
+    c.ph[7] -= 0;
     const int a = B.agent_order ? B.agent_order[qi] : qi;
     // instance of this agent: last i with inst_agent_ptr[i] <= a
     int lo = 0, hi = B.n_inst;
@@ -842,6 +875,7 @@ dsqp_refine_kernel(const DevBatch B, const DevOut O, const csdo_params P, const 
     c.active = c.t < Nt;
     c.has_next = c.t < Nt - 1;
     c.K = B.plane_ptr[a + 1] - B.plane_ptr[a];
+    c.pl = c.K <= c.KS ? c.pl_smem : c.pl_glob;
     c.plane_t = B.plane_t + B.plane_ptr[a];
     c.plane_abc = B.plane_abc + (size_t)12 * B.plane_ptr[a];
     c.No = B.obs_ptr[inst + 1] - B.obs_ptr[inst];
@@ -865,15 +899,18 @@ dsqp_refine_kernel(const DevBatch B, const DevOut O, const csdo_params P, const 
         c.cur[k * NT + c.t] = v;
         c.sol[k * NT + c.t] = v;
       }
-      c.ro[RO_TRX * NT + c.t] = c.guess[0 * Nt + c.t];
-      c.ro[RO_TRY * NT + c.t] = c.guess[1 * Nt + c.t];
+      c.ros[RO_TRX * NT + c.t] = c.guess[0 * Nt + c.t];
+      c.ros[RO_TRY * NT + c.t] = c.guess[1 * Nt + c.t];
     }
-    c.cfg[0] = c.guess[0]; c.cfg[1] = c.guess[Nt - 1];
-    c.cfg[2] = c.guess[Nt]; c.cfg[3] = c.guess[2 * Nt - 1];
-    c.cfg[4] = c.guess[2 * Nt]; c.cfg[5] = c.guess[3 * Nt - 1];
+    if (threadIdx.x == 0) {
+      c.cfgs[0] = c.guess[0]; c.cfgs[1] = c.guess[Nt - 1];
+      c.cfgs[2] = c.guess[Nt]; c.cfgs[3] = c.guess[2 * Nt - 1];
+      c.cfgs[4] = c.guess[2 * Nt]; c.cfgs[5] = c.guess[3 * Nt - 1];
+    }
     if (threadIdx.x == 0) s_flag = 0;
     __syncthreads();
     // calcCorridors (dsqp_solver.cc:1154) on float disc centres
+    PH_T0();
     if (agent_corridors(c, P, c.guess, c.guess + Nt, c.guess + 2 * Nt, 1, false, nullptr)) s_flag = 1;
     __syncthreads();
     if (threadIdx.x == 0 && s_flag) atomicAnd(&O.inst_static_legal[inst], 0);
@@ -882,9 +919,13 @@ dsqp_refine_kernel(const DevBatch B, const DevOut O, const csdo_params P, const 
     const double th = P.delta_solution_threshold;
     double delta = th + 1;
     int iter_count = 0, status = 1, admm = 0, nfac = 0;
+    __syncthreads();
+    PH_ADD(0);
     while (delta > th && iter_count < P.max_iter) {
       assemble_rows(c, P);
+      PH_ADD(1);
       const QpOut q = solve_qp(c, P);
+      ph_t0 = clock64();
       status = q.status; admm += q.iters; nfac += q.n_factor;
       double s[1] = {0.0};
       if (c.active) {
@@ -902,8 +943,10 @@ dsqp_refine_kernel(const DevBatch B, const DevOut O, const csdo_params P, const 
         for (int k = 0; k < 6; ++k) c.cur[k * NT + c.t] = c.sol[k * NT + c.t];
       __syncthreads();
       if (!P.fixed_corridor) {
+        PH_ADD(7);
         agent_corridors(c, P, c.sol, c.sol + NT, c.sol + 2 * NT, 0, true, nullptr);
         __syncthreads();
+        PH_ADD(0);
       }
     }
     // extractSingleSolutionVec2OptRes + per-agent records
@@ -926,7 +969,28 @@ dsqp_refine_kernel(const DevBatch B, const DevOut O, const csdo_params P, const 
       O.admm_iters[a] = admm; O.n_factor[a] = nfac; O.objective[a] = ob[0];
     }
     __syncthreads();
+    PH_ADD(7);
   }
+  if (threadIdx.x == 0) {
+    unsigned long long *prof = reinterpret_cast<unsigned long long *>(queue + 2);
+    for (int k = 0; k < 8; ++k) atomicAdd(prof + k, (unsigned long long)c.ph[k]);
+  }
+}
+
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
+dsqp_refine_kernel(const DevBatch B, const DevOut O, const csdo_params P, const Layout LY, double *scratch,
+                   int *queue) {
+  refine_body(B, O, P, LY, scratch, queue);
+}
+
+using RefineKernel = void (*)(const DevBatch, const DevOut, const csdo_params, const Layout, double *, int *);
+static RefineKernel pick_kernel(int block) {
+  if (block <= 64) return dsqp_refine_kernel<64, 4>;
+  if (block <= 96) return dsqp_refine_kernel<96, 2>;
+  if (block <= 128) return dsqp_refine_kernel<128, 2>;
+  if (block <= 256) return dsqp_refine_kernel<256, 1>;
+  return dsqp_refine_kernel<512, 1>;
 }
 
 // status aggregation of SolverDSQP (dsqp_solver.cc:1224-1243), one thread per instance
@@ -975,24 +1039,26 @@ __global__ void corridors_kernel(const DevBatch B, const csdo_params P, int doub
 // ===================================================================
 // host-side launchers (called from csdo_api.cpp through dsqp_launch.h)
 // ===================================================================
-Layout make_layout(int NT, int KMAX, int tier) {
+Layout make_layout(int NT, int KMAX, int tier, int KS) {
   Layout l{};
-  l.NT = NT; l.KMAX = KMAX; l.tier = tier;
+  l.NT = NT; l.KMAX = KMAX; l.tier = tier; l.KS = KS;
   int o = 0;
   auto take = [&](int n) { int r = o; o += (n + 1) & ~1; return r; };
   l.o_x = take(6 * NT); l.o_xt = take(6 * NT); l.o_rhs = take(6 * NT); l.o_D = take(6 * NT);
-  l.o_carry = take(4 * NT); l.o_w = take(13 * NT + 8); l.o_E = take(13 * NT + 8);
-  l.o_red = take(32 * N_COUNT);
+  l.o_carry = take(4 * NT);
+  l.o_ro = take(RO_COUNT * NT + 8);
+  l.o_E = take(16 * NT);
+  l.o_w = take(16 * NT);
+  l.o_red = take(((NT + 31) / 32 + 1) * N_COUNT);
   l.o_pstart = take((NT + 2 + 1) / 2);
   l.o_sinv = take(kMaxNs * kMaxNs + 3 * kMaxNs);
   l.o_L = tier < 2 ? take(kLw * 6 * NT) : 0;
-  l.o_ro = tier < 1 ? take(RO_COUNT * NT) : 0;
+  l.o_pl = take(PL_COUNT * 4 * KS);
   l.smem_doubles = o;
   size_t g = 0;
   auto gtake = [&](size_t n) { size_t r = g; g += (n + 1) & ~(size_t)1; return r; };
-  l.g_cur = gtake(6 * (size_t)NT); l.g_sol = gtake(6 * (size_t)NT); l.g_dy = gtake(13 * (size_t)NT + 8);
+  l.g_cur = gtake(6 * (size_t)NT); l.g_sol = gtake(6 * (size_t)NT); l.g_dy = gtake(16 * (size_t)NT);
   l.g_pl = gtake((size_t)PL_COUNT * 4 * KMAX);
-  l.g_ro = gtake((size_t)RO_COUNT * NT);
   l.g_L = gtake((size_t)kLw * 6 * NT);
   l.slot_doubles = g;
   return l;
@@ -1001,13 +1067,14 @@ Layout make_layout(int NT, int KMAX, int tier) {
 cudaError_t launch_refine(const DevBatch &B, const DevOut &O, const csdo_params &P, const Layout &LY,
                           double *scratch, int *queue, int grid, int block, cudaStream_t stream) {
   const int smem = LY.smem_doubles * 8;
-  cudaError_t e = cudaFuncSetAttribute(dsqp_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  RefineKernel kern = pick_kernel(block);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
-  e = cudaMemsetAsync(queue, 0, sizeof(int), stream);
+  e = cudaMemsetAsync(queue, 0, 2048, stream);
   if (e != cudaSuccess) return e;
   const int fb = 256;
   fill_int_kernel<<<(B.n_inst + fb - 1) / fb, fb, 0, stream>>>(O.inst_static_legal, B.n_inst, 1);
-  dsqp_refine_kernel<<<grid, block, smem, stream>>>(B, O, P, LY, scratch, queue);
+  kern<<<grid, block, smem, stream>>>(B, O, P, LY, scratch, queue);
   aggregate_status_kernel<<<(B.n_inst + fb - 1) / fb, fb, 0, stream>>>(B, O);
   return cudaGetLastError();
 }
@@ -1022,18 +1089,22 @@ cudaError_t launch_corridors(const DevBatch &B, const csdo_params &P, int double
 }
 
 int refine_occupancy(int block, int smem_bytes) {
-  if (cudaFuncSetAttribute(dsqp_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) !=
-      cudaSuccess)
-    return 0;
+  RefineKernel kern = pick_kernel(block);
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) return 0;
   int n = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, dsqp_refine_kernel, block, smem_bytes) != cudaSuccess)
-    return 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, block, smem_bytes) != cudaSuccess) return 0;
   return n;
 }
 
-int refine_kernel_regs() {
+void read_debug_counters(unsigned long long *out16) {
+  cudaMemcpyFromSymbol(out16, g_dbg, 16 * sizeof(unsigned long long));
+  unsigned long long z[16] = {0};
+  cudaMemcpyToSymbol(g_dbg, z, sizeof(z));
+}
+
+int refine_kernel_regs(int block) {
   cudaFuncAttributes fa;
-  if (cudaFuncGetAttributes(&fa, dsqp_refine_kernel) != cudaSuccess) return -1;
+  if (cudaFuncGetAttributes(&fa, pick_kernel(block)) != cudaSuccess) return -1;
   return fa.numRegs;
 }
 
