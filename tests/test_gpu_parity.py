@@ -222,3 +222,35 @@ def test_errors_are_reported(params, solver):
     with pytest.raises(binding.CsdoError) as e:
         solver.refine(b)
     assert e.value.code == binding.CSDO_ERR_UNSUPPORTED
+
+
+def test_cpp_solver_dsqp_shim(oracle, params, solver, tmp_path):
+    """include/csdo/dsqp_solver.h (the reference-shaped C++ class) gives the same result as the C ABI."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpp", "test_solver_dsqp")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.dirname(exe)])
+    ins = synthetic_instance(131, 50.0, 4, 8, (8, 12), params)
+    na, nt = ins.n_agents, ins.nt
+    f = tmp_path / "guess.txt"
+    with open(f, "w") as fh:
+        fh.write(f"{na} {nt} {ins.dimx!r} {ins.dimy!r} {ins.obstacles.shape[0]}\n")
+        for o in ins.obstacles:
+            fh.write(" ".join(repr(float(v)) for v in o) + "\n")
+        for a in range(na):
+            for t in range(nt):
+                fh.write(" ".join(repr(float(ins.guess[a, k, t])) for k in range(6)) + "\n")
+    out = subprocess.run([exe, str(f)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.strip().splitlines()
+    pb, legal = solver.planes(pack_instances([ins]))
+    rg = solver.refine(pb)
+    head = lines[0].split()
+    assert int(head[1]) == rg.inst_status[0] and int(head[3]) == rg.inst_static_legal[0] and int(head[5]) == legal[0]
+    for a in range(na):
+        tok = lines[1 + a].split()
+        assert int(tok[2]) == rg.status[a] and int(tok[3]) == rg.sqp_iters[a]
+        assert int(tok[4]) == pb.plane_ptr[a + 1] - pb.plane_ptr[a]
+        vals = np.array([float(v) for v in tok[5:]]).reshape(nt, 2)
+        assert np.array_equal(vals[:, 0], rg.agent_traj(pb, a)[0])          # x(t), bit for bit
+        assert np.array_equal(vals[:, 1], rg.agent_corridor(pb, a)[0])      # xf_min(t)
