@@ -42,7 +42,28 @@ struct Parts {
   __device__ __forceinline__ int len(int p) const { return base + (p < rem ? 1 : 0); }
   __device__ __forceinline__ int start(int p) const { return p * (base + 1) + (p < rem ? p : rem); }
   __device__ __forceinline__ int sep(int j) const { return start(j) + len(j); }  // block index of separator j
+  // Bank skew (in doubles) of the rows of partition p / separator p: the lanes of the solver warp read
+  // their blocks with LDS.128 in lockstep; shifting partition p so that its rows start at 16-byte
+  // slot p (mod 8) of the 128-byte bank window makes those 8 loads conflict-free (a block is 288 B).
+  // The offsets accumulate (each partition is pushed 0..7 slots further than the previous one), so the
+  // shifted partitions never overlap.
+  int off[8];
+  const int *tab = nullptr;  // optional copy of off[] in shared memory (cheap runtime indexing)
+  __device__ __forceinline__ int skew(int p) const {
+    if (tab) return tab[p];
+    int r = 0;  // select chain: keeps off[] in registers
+#pragma unroll
+    for (int q = 0; q < 8; ++q) r = (q == p) ? off[q] : r;
+    return r;
+  }
+  // partition that owns block t (a separator belongs to the partition above it)
+  __device__ __forceinline__ int owner(int t) const {
+    const int big = rem * (base + 2);
+    return t < big ? t / (base + 2) : rem + (t - big) / (base + 1);
+  }
+  __device__ __forceinline__ int skew_of_block(int t) const { return P == 1 ? 0 : skew(owner(t)); }
 };
+constexpr int kSkewPad = 128;  // extra doubles at the end of the L6 area (<= 8 partitions x 14 doubles)
 
 __device__ __forceinline__ Parts make_parts(int Nt) {
   Parts q;
@@ -52,6 +73,12 @@ __device__ __forceinline__ Parts make_parts(int Nt) {
   const int interior = Nt - (P - 1);
   q.base = interior / P;
   q.rem = interior % P;
+  int acc16 = 0;  // accumulated shift in 16-byte slots
+#pragma unroll
+  for (int p = 0; p < 8; ++p) {
+    if (p < P && P > 1) acc16 += (p - (18 * q.start(p) + acc16)) & 7;
+    q.off[p] = 2 * acc16;
+  }
   return q;
 }
 
@@ -155,7 +182,7 @@ __device__ __forceinline__ double coupling(const double *L6, int tr, int kr, int
 
 // ---- F2: Schur complement contributions of partition p, streamed ----
 __device__ void schur_partition(const BandMem &bm, const Parts &pt, int p) {
-  const double *L6 = bm.L6, *dinv = bm.dinv;
+  const double *L6 = bm.L6 + pt.skew(p), *dinv = bm.dinv;  // own rows and the next separator (same skew)
   const int t0 = pt.start(p), t1 = t0 + pt.len(p);
   double *GCC = bm.G + p * 78, *GBB = GCC + 21, *GBC = GBB + 21;
   double win[6][6];  // win[a][k]: y of column a (coupling to previous separator unknown a) at the last block seen
@@ -247,9 +274,16 @@ template <bool SH>
 __device__ __noinline__ void band_factor_warp(const BandMem bm, int Nt) {
   if (SH) { __builtin_assume(__isShared(bm.L6)); __builtin_assume(__isShared(bm.dinv)); }
   __builtin_assume(__isShared(bm.Sinv)); __builtin_assume(__isShared(bm.sv)); __builtin_assume(__isShared(bm.G));
-  const Parts pt = make_parts(Nt);
+  Parts pt = make_parts(Nt);
   const int lane = threadIdx.x & 31;
-  if (lane < pt.P) interior_factor(bm.L6, bm.dinv, pt.start(lane), pt.start(lane) + pt.len(lane));
+  {
+    int *tab = reinterpret_cast<int *>(bm.sv + 3 * kMaxNs);
+    if (lane < 8) tab[lane] = pt.skew(lane);
+    __syncwarp();
+    pt.tab = tab;
+  }
+  if (lane < pt.P)
+    interior_factor(bm.L6 + (pt.P == 1 ? 0 : pt.skew(lane)), bm.dinv, pt.start(lane), pt.start(lane) + pt.len(lane));
   __syncwarp();
   if (pt.P == 1) return;
   if (lane < pt.P) schur_partition(bm, pt, lane);
@@ -264,7 +298,7 @@ __device__ __noinline__ void band_factor_warp(const BandMem bm, int Nt) {
     const int T = pt.sep(j);
     // diagonal block: H_TT - GBB(partition j) - GCC(partition j+1)
     const int hi = a > b ? a : b, lo = a > b ? b : a;
-    double v = (a == b) ? bm.dinv[6 * T + a] : bm.L6[(size_t)(6 * T + hi) * 6 + (hi - lo) - 1];
+    double v = (a == b) ? bm.dinv[6 * T + a] : bm.L6[pt.skew(j) + (size_t)(6 * T + hi) * 6 + (hi - lo) - 1];
     const int q = hi * (hi + 1) / 2 + lo;
     v -= bm.G[j * 78 + 21 + q];
     v -= bm.G[(j + 1) * 78 + q];
@@ -299,8 +333,14 @@ __device__ __noinline__ void band_solve_warp(const BandMem bm, double *rhs, doub
   if (SH) { __builtin_assume(__isShared(bm.L6)); __builtin_assume(__isShared(bm.dinv)); }
   __builtin_assume(__isShared(bm.Sinv)); __builtin_assume(__isShared(bm.sv));
   __builtin_assume(__isShared(rhs)); __builtin_assume(__isShared(tmp));
-  const Parts pt = make_parts(Nt);
+  Parts pt = make_parts(Nt);
   const int lane = threadIdx.x & 31;
+  {
+    int *tab = reinterpret_cast<int *>(bm.sv + 3 * kMaxNs);
+    if (lane < 8) tab[lane] = pt.skew(lane);
+    __syncwarp();
+    pt.tab = tab;
+  }
   if (pt.P == 1) {
     if (lane == 0) interior_solve(bm.L6, bm.dinv, rhs, rhs, 0, Nt, NT);
     __syncwarp();
@@ -308,7 +348,8 @@ __device__ __noinline__ void band_solve_warp(const BandMem bm, double *rhs, doub
   }
   long long dbg_t0 = clock64();
   const int t0 = pt.start(lane < pt.P ? lane : 0), t1 = t0 + pt.len(lane < pt.P ? lane : 0);
-  if (lane < pt.P) interior_solve(bm.L6, bm.dinv, rhs, tmp, t0, t1, NT);  // S1
+  const int sk = pt.skew(lane < pt.P ? lane : 0);
+  if (lane < pt.P) interior_solve(bm.L6 + sk, bm.dinv, rhs, tmp, t0, t1, NT);  // S1
   __syncwarp();
   DBG_T(0);
   const int Ns = 6 * (pt.P - 1);
@@ -318,10 +359,10 @@ __device__ __noinline__ void band_solve_warp(const BandMem bm, double *rhs, doub
     double s = rhs[k * NT + T];
 #pragma unroll
     for (int kc = 0; kc < 6; ++kc)
-      if (kc >= k) s = fma(-coupling(bm.L6, T, k, kc), tmp[kc * NT + T - 1], s);
+      if (kc >= k) s = fma(-coupling(bm.L6 + pt.skew(j), T, k, kc), tmp[kc * NT + T - 1], s);
 #pragma unroll
     for (int kr = 0; kr < 6; ++kr)
-      if (kr <= k) s = fma(-coupling(bm.L6, T + 1, kr, k), tmp[kr * NT + T + 1], s);
+      if (kr <= k) s = fma(-coupling(bm.L6 + pt.skew(j + 1), T + 1, kr, k), tmp[kr * NT + T + 1], s);
     g[e] = s;
   }
   __syncwarp();
@@ -347,7 +388,7 @@ __device__ __noinline__ void band_solve_warp(const BandMem bm, double *rhs, doub
         double a = rhs[k * NT + t0];
 #pragma unroll
         for (int kc = 0; kc < 6; ++kc)
-          if (kc >= k) a = fma(-coupling(bm.L6, t0, k, kc), xp[kc], a);
+          if (kc >= k) a = fma(-coupling(bm.L6 + sk, t0, k, kc), xp[kc], a);
         rhs[k * NT + t0] = a;
       }
     }
@@ -358,11 +399,11 @@ __device__ __noinline__ void band_solve_warp(const BandMem bm, double *rhs, doub
         double a = rhs[kc * NT + t1 - 1];
 #pragma unroll
         for (int kr = 0; kr < 6; ++kr)
-          if (kr <= kc) a = fma(-coupling(bm.L6, t1, kr, kc), xn[kr], a);
+          if (kr <= kc) a = fma(-coupling(bm.L6 + sk, t1, kr, kc), xn[kr], a);
         rhs[kc * NT + t1 - 1] = a;
       }
     }
-    interior_solve(bm.L6, bm.dinv, rhs, rhs, t0, t1, NT);
+    interior_solve(bm.L6 + sk, bm.dinv, rhs, rhs, t0, t1, NT);
   }
   __syncwarp();
   DBG_T(3);

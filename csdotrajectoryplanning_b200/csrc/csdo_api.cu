@@ -168,6 +168,7 @@ int run_refine(csdo_handle *h, const DevBatch &B, const DevOut &O, int max_nt, i
     if (refine_occupancy(block, l.smem_doubles * 8) >= occ) LY = l;
   }
   if (occ < 1) { h->err = "horizon does not fit the kernel's shared-memory layout"; return CSDO_ERR_UNSUPPORTED; }
+  if (const char *cap = getenv("CSDO_MAX_CTAS_PER_SM")) occ = std::max(1, std::min(occ, atoi(cap)));  // developer knob
   const int grid = std::min(B.n_agents, h->num_sms * occ);
   int rc;
   if ((rc = ensure(h, h->scratch, (size_t)grid * LY.slot_doubles * sizeof(double)))) return rc;

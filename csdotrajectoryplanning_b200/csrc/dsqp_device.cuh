@@ -41,23 +41,23 @@ struct BandMem {
   double *G;          // factor-time scratch: per partition GCC[21] GBB[21] GBC[36] (shared)
 };
 
-struct Ctx {
-  int Nt, NT, K, KP, No, tid, nthr, t;  // t = this thread's time step (tid), valid if tid < Nt
-  bool active, has_next, l_shared;
-  int solver_warp;  // the warp of this CTA that runs the band factor/solve
+// CTA-uniform context of the agent being refined.  It lives in SHARED memory (written by thread 0
+// between barriers): keeping two dozen pointers per thread in registers starved the row passes.
+struct CtxShared {
+  int Nt, NT, K, KP, No, KS, solver_warp;
+  bool l_shared;
   // shared-memory vectors, SoA with stride NT: v[k*NT + t]
   double *x, *xt, *rhs, *D, *carry, *red;
-  int *pstart;  // [Nt+1] first plane of each step
-  double *ros;  // read-only per-step row data, RO_COUNT planes (shared)
-  double *cfgs; // 6 start/goal pins (shared)
-  double *Es;   // Ruiz row scaling of the fixed rows, 16 planes (shared; read-only during the ADMM loop)
-  double *ws;   // ADMM row state w = z_hat + y/rho of the fixed rows, 16 planes (shared)
-  BandMem bm;   // band factor storage (band_solver.cuh)
+  int *pstart;   // [Nt+1] first plane of each step
+  double *ros;   // read-only per-step row data, RO_COUNT planes
+  double *cfgs;  // 6 start/goal pins
+  double *Es;    // Ruiz row scaling of the fixed rows, 16 planes (read-only during the ADMM loop)
+  double *ws;    // ADMM row state w = z_hat + y/rho of the fixed rows, 16 planes
+  BandMem bm;    // band factor storage (band_solver.cuh)
   // per-CTA global scratch
   double *cur, *sol, *dy;
-  double *pl;       // plane rows of this agent: shared memory when they fit (K <= KS), else global scratch
+  double *pl;    // plane rows of this agent: shared memory when they fit (K <= KS), else global scratch
   double *pl_smem, *pl_glob;
-  int KS;
   // batch views of this agent
   const double *guess;      // 6 planes, stride Nt
   const double *plane_abc;  // [K][12]
@@ -65,8 +65,31 @@ struct Ctx {
   const double *obs;        // [No][3]
   double *corr;             // 8 planes, stride Nt (output array doubles as the live corridor)
   double dimx, dimy;
-  double rho, c;  // current rho and Ruiz cost scaling
-  long long ph[8];  // phase cycle counters (thread 0 is the one reported)
+};
+
+// Per-thread handle: the shared context plus the few values that change inside a QP.
+struct Ctx {
+  CtxShared *s;
+  double rho, c;    // current rho and Ruiz cost scaling (every thread holds the same value)
+  long long ph[8];  // phase cycle counters (developer profiling)
+#define CSDO_GET(type, name) __device__ __forceinline__ type name() const { return s->name; }
+  CSDO_GET(int, Nt) CSDO_GET(int, NT) CSDO_GET(int, K) CSDO_GET(int, KP) CSDO_GET(int, No) CSDO_GET(int, KS)
+  CSDO_GET(int, solver_warp) CSDO_GET(bool, l_shared)
+  CSDO_GET(double *, x) CSDO_GET(double *, xt) CSDO_GET(double *, rhs) CSDO_GET(double *, D)
+  CSDO_GET(double *, carry) CSDO_GET(double *, red) CSDO_GET(int *, pstart) CSDO_GET(double *, ros)
+  CSDO_GET(double *, cfgs) CSDO_GET(double *, Es) CSDO_GET(double *, ws)
+  CSDO_GET(double *, cur) CSDO_GET(double *, sol) CSDO_GET(double *, dy) CSDO_GET(double *, pl)
+  CSDO_GET(double *, pl_smem) CSDO_GET(double *, pl_glob)
+  CSDO_GET(const double *, guess) CSDO_GET(const double *, plane_abc) CSDO_GET(const int *, plane_t)
+  CSDO_GET(const double *, obs) CSDO_GET(double *, corr) CSDO_GET(double, dimx) CSDO_GET(double, dimy)
+#undef CSDO_GET
+  __device__ __forceinline__ const BandMem &bm() const { return s->bm; }
+  // one thread per time step
+  __device__ __forceinline__ int tid() const { return threadIdx.x; }
+  __device__ __forceinline__ int nthr() const { return blockDim.x; }
+  __device__ __forceinline__ int t() const { return threadIdx.x; }
+  __device__ __forceinline__ bool active() const { return (int)threadIdx.x < s->Nt; }
+  __device__ __forceinline__ bool has_next() const { return (int)threadIdx.x < s->Nt - 1; }
 };
 
 __device__ __forceinline__ double limit_scaling(double v) {
@@ -108,60 +131,77 @@ __device__ __forceinline__ void block_reduce(double (&v)[N], double *red) {
 // NC coefficients on local unknowns i*, raw bounds l,u, the row's ADMM state w and Ruiz factor E.
 template <class F>
 __device__ __forceinline__ void visit_rows(Ctx &c, const csdo_params &P, F &f) {
-  const int t = c.t;
-  __builtin_assume(__isShared(c.ros));
-  __builtin_assume(__isShared(c.cfgs));
-  __builtin_assume(__isShared(c.Es));
-  __builtin_assume(__isShared(c.ws));
-  __builtin_assume(__isShared(c.pstart));
-  const double *ro_ = c.ros + t;
-  const int NTs = c.NT;
+  const int t = c.t();
+  __builtin_assume(__isShared(c.ros()));
+  __builtin_assume(__isShared(c.cfgs()));
+  __builtin_assume(__isShared(c.Es()));
+  __builtin_assume(__isShared(c.ws()));
+  __builtin_assume(__isShared(c.pstart()));
+  const double *ro_ = c.ros() + t;
+  const int NTs = c.NT();
 #define RO(i) ro_[(i) * NTs]
   const double sn = RO(RO_SN), cs = RO(RO_CS);
-  if (c.has_next) {
+  if (c.has_next()) {
     // calcKineConstraint :646-744, lb = ub = -C
-    f.template row<4>(0, VX, 1.0, VP, RO(RO_A1), VV, P.dt * cs, NX, -1.0, RO(RO_KR0), RO(RO_KR0), c.ws[0 * c.NT + t], c.Es[0 * c.NT + t]);
-    f.template row<4>(1, VY, 1.0, VP, RO(RO_A2), VV, P.dt * sn, NY, -1.0, RO(RO_KR1), RO(RO_KR1), c.ws[1 * c.NT + t], c.Es[1 * c.NT + t]);
-    f.template row<4>(2, VP, 1.0, VS, RO(RO_A3), VV, RO(RO_B3), NP, -1.0, RO(RO_KR2), RO(RO_KR2), c.ws[2 * c.NT + t], c.Es[2 * c.NT + t]);
-    f.template row<3>(3, VS, 1.0, VW, P.dt * 1.0, NS, -1.0, 0, 0.0, -0.0, -0.0, c.ws[3 * c.NT + t], c.Es[3 * c.NT + t]);
+    f.template row<4>(0, VX, 1.0, VP, RO(RO_A1), VV, P.dt * cs, NX, -1.0, RO(RO_KR0), RO(RO_KR0), c.ws()[0 * c.NT() + t], c.Es()[0 * c.NT() + t]);
+    f.template row<4>(1, VY, 1.0, VP, RO(RO_A2), VV, P.dt * sn, NY, -1.0, RO(RO_KR1), RO(RO_KR1), c.ws()[1 * c.NT() + t], c.Es()[1 * c.NT() + t]);
+    f.template row<4>(2, VP, 1.0, VS, RO(RO_A3), VV, RO(RO_B3), NP, -1.0, RO(RO_KR2), RO(RO_KR2), c.ws()[2 * c.NT() + t], c.Es()[2 * c.NT() + t]);
+    f.template row<3>(3, VS, 1.0, VW, P.dt * 1.0, NS, -1.0, 0, 0.0, -0.0, -0.0, c.ws()[3 * c.NT() + t], c.Es()[3 * c.NT() + t]);
   }
   // calcCfgConstraint :746-788 (cfg = x0,xN,y0,yN,yaw0,yawN); rows 13..15 of the first/last step
   if (t == 0) {
-    f.template row<1>(13, VX, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, c.cfgs[0], c.cfgs[0], c.ws[13 * c.NT + t], c.Es[13 * c.NT + t]);
-    f.template row<1>(14, VY, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, c.cfgs[2], c.cfgs[2], c.ws[14 * c.NT + t], c.Es[14 * c.NT + t]);
-    f.template row<1>(15, VP, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, c.cfgs[4], c.cfgs[4], c.ws[15 * c.NT + t], c.Es[15 * c.NT + t]);
+    f.template row<1>(13, VX, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, c.cfgs()[0], c.cfgs()[0], c.ws()[13 * c.NT() + t], c.Es()[13 * c.NT() + t]);
+    f.template row<1>(14, VY, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, c.cfgs()[2], c.cfgs()[2], c.ws()[14 * c.NT() + t], c.Es()[14 * c.NT() + t]);
+    f.template row<1>(15, VP, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, c.cfgs()[4], c.cfgs()[4], c.ws()[15 * c.NT() + t], c.Es()[15 * c.NT() + t]);
   }
-  if (t == c.Nt - 1) {
-    f.template row<1>(13, VX, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, c.cfgs[1], c.cfgs[1], c.ws[13 * c.NT + t], c.Es[13 * c.NT + t]);
-    f.template row<1>(14, VY, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, c.cfgs[3], c.cfgs[3], c.ws[14 * c.NT + t], c.Es[14 * c.NT + t]);
-    f.template row<1>(15, VP, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, c.cfgs[5], c.cfgs[5], c.ws[15 * c.NT + t], c.Es[15 * c.NT + t]);
+  if (t == c.Nt() - 1) {
+    f.template row<1>(13, VX, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, c.cfgs()[1], c.cfgs()[1], c.ws()[13 * c.NT() + t], c.Es()[13 * c.NT() + t]);
+    f.template row<1>(14, VY, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, c.cfgs()[3], c.cfgs()[3], c.ws()[14 * c.NT() + t], c.Es()[14 * c.NT() + t]);
+    f.template row<1>(15, VP, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, c.cfgs()[5], c.cfgs()[5], c.ws()[15 * c.NT() + t], c.Es()[15 * c.NT() + t]);
   }
   // calcCorridorConstraint :874-968: D = [I,0,-f2x sin; 0,I,f2x cos; I,0,-r2x sin; 0,I,r2x cos]
-  f.template row<2>(4, VX, 1.0, VP, -P.f2x * sn, 0, 0.0, 0, 0.0, RO(RO_CL0), RO(RO_CU0), c.ws[4 * c.NT + t], c.Es[4 * c.NT + t]);
-  f.template row<2>(5, VY, 1.0, VP, P.f2x * cs, 0, 0.0, 0, 0.0, RO(RO_CL1), RO(RO_CU1), c.ws[5 * c.NT + t], c.Es[5 * c.NT + t]);
-  f.template row<2>(6, VX, 1.0, VP, -P.r2x * sn, 0, 0.0, 0, 0.0, RO(RO_CL2), RO(RO_CU2), c.ws[6 * c.NT + t], c.Es[6 * c.NT + t]);
-  f.template row<2>(7, VY, 1.0, VP, P.r2x * cs, 0, 0.0, 0, 0.0, RO(RO_CL3), RO(RO_CU3), c.ws[7 * c.NT + t], c.Es[7 * c.NT + t]);
+  f.template row<2>(4, VX, 1.0, VP, -P.f2x * sn, 0, 0.0, 0, 0.0, RO(RO_CL0), RO(RO_CU0), c.ws()[4 * c.NT() + t], c.Es()[4 * c.NT() + t]);
+  f.template row<2>(5, VY, 1.0, VP, P.f2x * cs, 0, 0.0, 0, 0.0, RO(RO_CL1), RO(RO_CU1), c.ws()[5 * c.NT() + t], c.Es()[5 * c.NT() + t]);
+  f.template row<2>(6, VX, 1.0, VP, -P.r2x * sn, 0, 0.0, 0, 0.0, RO(RO_CL2), RO(RO_CU2), c.ws()[6 * c.NT() + t], c.Es()[6 * c.NT() + t]);
+  f.template row<2>(7, VY, 1.0, VP, P.r2x * cs, 0, 0.0, 0, 0.0, RO(RO_CL3), RO(RO_CU3), c.ws()[7 * c.NT() + t], c.Es()[7 * c.NT() + t]);
   // calcTrustRegionConstraint :970-994 (centre = initial guess, all SQP iterations)
-  f.template row<1>(8, VX, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, -P.r_trust + RO(RO_TRX), P.r_trust + RO(RO_TRX), c.ws[8 * c.NT + t], c.Es[8 * c.NT + t]);
-  f.template row<1>(9, VY, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, -P.r_trust + RO(RO_TRY), P.r_trust + RO(RO_TRY), c.ws[9 * c.NT + t], c.Es[9 * c.NT + t]);
+  f.template row<1>(8, VX, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, -P.r_trust + RO(RO_TRX), P.r_trust + RO(RO_TRX), c.ws()[8 * c.NT() + t], c.Es()[8 * c.NT() + t]);
+  f.template row<1>(9, VY, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, -P.r_trust + RO(RO_TRY), P.r_trust + RO(RO_TRY), c.ws()[9 * c.NT() + t], c.Es()[9 * c.NT() + t]);
   // calcMaxCtrlAndSteerConstraint :996-1039
-  if (c.has_next) {
-    f.template row<1>(10, VV, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, -P.max_v, P.max_v, c.ws[10 * c.NT + t], c.Es[10 * c.NT + t]);
-    f.template row<1>(11, VW, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, -P.max_omega, P.max_omega, c.ws[11 * c.NT + t], c.Es[11 * c.NT + t]);
+  if (c.has_next()) {
+    f.template row<1>(10, VV, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, -P.max_v, P.max_v, c.ws()[10 * c.NT() + t], c.Es()[10 * c.NT() + t]);
+    f.template row<1>(11, VW, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, -P.max_omega, P.max_omega, c.ws()[11 * c.NT() + t], c.Es()[11 * c.NT() + t]);
   }
-  f.template row<1>(12, VS, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, -P.steer_max, P.steer_max, c.ws[12 * c.NT + t], c.Es[12 * c.NT + t]);
+  f.template row<1>(12, VS, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, -P.steer_max, P.steer_max, c.ws()[12 * c.NT() + t], c.Es()[12 * c.NT() + t]);
   // calcInterVehicleConstraint :1097-1129: 4 rows per plane of this step, l = -inf
-  const int k0 = c.pstart[t], k1 = c.pstart[t + 1];
-  if (c.pl == c.pl_smem) {  // on-chip plane rows: plain shared-memory loads (LDS), not generic ones
-    __builtin_assume(__isShared(c.pl_smem));
+  const int k0 = c.pstart()[t], k1 = c.pstart()[t + 1];
+  if (c.pl() == c.pl_smem()) {  // on-chip plane rows: plain shared-memory loads (LDS), not generic ones
+    __builtin_assume(__isShared(c.pl_smem()));
     for (int r = 4 * k0; r < 4 * k1; ++r) {
-      double *q = c.pl_smem + (size_t)PL_COUNT * r;
+      double *q = c.pl_smem() + (size_t)PL_COUNT * r;
       f.template row<3>(-1, VX, q[PL_A], VY, q[PL_B], VP, q[PL_G], 0, 0.0, -INFINITY, q[PL_U], q[PL_W], q[PL_E]);
     }
   } else {
-    for (int r = 4 * k0; r < 4 * k1; ++r) {
-      double *q = c.pl_glob + (size_t)PL_COUNT * r;
-      f.template row<3>(-1, VX, q[PL_A], VY, q[PL_B], VP, q[PL_G], 0, 0.0, -INFINITY, q[PL_U], q[PL_W], q[PL_E]);
+    // overflow plane rows live in global scratch (L2 latency): one plane = 4 rows = 12 16-byte loads
+    // issued together, processed from registers, w and E written back together
+    for (int k = k0; k < k1; ++k) {
+      double2 *q2 = reinterpret_cast<double2 *>(c.pl_glob() + (size_t)PL_COUNT * 4 * k);
+      double v[4][PL_COUNT];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int h = 0; h < PL_COUNT / 2; ++h) {
+          const double2 d2 = q2[r * (PL_COUNT / 2) + h];
+          v[r][2 * h] = d2.x;
+          v[r][2 * h + 1] = d2.y;
+        }
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        f.template row<3>(-1, VX, v[r][PL_A], VY, v[r][PL_B], VP, v[r][PL_G], 0, 0.0, -INFINITY, v[r][PL_U],
+                          v[r][PL_W], v[r][PL_E]);
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        q2[r * (PL_COUNT / 2) + PL_E / 2] = make_double2(v[r][PL_E], v[r][PL_W]);
     }
   }
 #undef RO

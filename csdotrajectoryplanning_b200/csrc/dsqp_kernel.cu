@@ -10,8 +10,19 @@
 #include "dsqp_device.cuh"
 #include "band_solver.cuh"
 #include "dsqp_launch.h"
+#include <cstdlib>
 
 namespace csdo {
+
+// The band factor/solve are entered through function pointers read from device memory: an indirect
+// call follows the full ABI, so the callee may use the whole register file (a direct call to the
+// kernel-local clone leaves it only the ~77 registers that are not live in the caller, which makes the
+// sweeps 1.6-3x slower); the solver warp saves/restores its live registers around the call instead.
+using BandSolveFn = void (*)(const BandMem, double *, double *, int, int);
+using BandFactorFn = void (*)(const BandMem, int);
+__device__ BandSolveFn g_band_solve[2] = {band_solve_warp<false>, band_solve_warp<true>};
+__device__ BandFactorFn g_band_factor[2] = {band_factor_warp<false>, band_factor_warp<true>};
+
 
 // ===================================================================
 // corridor boxes (sqp/corridor.cc) -- adds/compares only, bit-exact
@@ -135,9 +146,9 @@ __device__ void generate_box(double x, double y, const ObsView &ov, double dimx,
 __device__ int agent_corridors(const Ctx &c, const csdo_params &P, const double *xs, const double *ys,
                                const double *yaws, int stride_is_nt, bool double_centres, int *box_status) {
   (void)stride_is_nt;
-  ObsView ov{c.obs, c.No, P.rv};
+  ObsView ov{c.obs(), c.No(), P.rv};
   int illegal = 0;
-  for (int b = c.tid; b < 2 * c.Nt; b += c.nthr) {
+  for (int b = c.tid(); b < 2 * c.Nt(); b += c.nthr()) {
     const int t = b >> 1, rear = b & 1;
     const double off = rear ? P.r2x : P.f2x;
     // separate multiply and add (the reference build has no FMA contraction)
@@ -148,13 +159,13 @@ __device__ int agent_corridors(const Ctx &c, const csdo_params &P, const double 
       cy = (double)(float)cy;
     }
     Box bx; int ok, init;
-    generate_box(cx, cy, ov, c.dimx, c.dimy, P, bx, ok, init);
+    generate_box(cx, cy, ov, c.dimx(), c.dimy(), P, bx, ok, init);
     if (init > 0) illegal = 1;
     const int base = rear ? 4 : 0;
-    c.corr[(base + 0) * c.Nt + t] = bx.x_min;
-    c.corr[(base + 1) * c.Nt + t] = bx.x_max;
-    c.corr[(base + 2) * c.Nt + t] = bx.y_min;
-    c.corr[(base + 3) * c.Nt + t] = bx.y_max;
+    c.corr()[(base + 0) * c.Nt() + t] = bx.x_min;
+    c.corr()[(base + 1) * c.Nt() + t] = bx.x_max;
+    c.corr()[(base + 2) * c.Nt() + t] = bx.y_min;
+    c.corr()[(base + 3) * c.Nt() + t] = bx.y_max;
     if (box_status) { box_status[2 * b] = ok; box_status[2 * b + 1] = init; }
   }
   return illegal;
@@ -326,49 +337,49 @@ struct HasmF {
 // QP phases
 // ===================================================================
 __device__ __forceinline__ void load_xv(const Ctx &c, const double *v, double (&xv)[10]) {
-  const int NT = c.NT, t = c.t;
+  const int NT = c.NT(), t = c.t();
 #pragma unroll
   for (int k = 0; k < 6; ++k) xv[k] = v[k * NT + t];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) xv[6 + k] = c.has_next ? v[k * NT + t + 1] : 0.0;
+  for (int k = 0; k < 4; ++k) xv[6 + k] = c.has_next() ? v[k * NT + t + 1] : 0.0;
 }
 
 // number of unknowns of step t (the last step has no v, w)
-__device__ __forceinline__ int nvar(const Ctx &c) { return c.has_next ? 6 : 4; }
+__device__ __forceinline__ int nvar(const Ctx &c) { return c.has_next() ? 6 : 4; }
 
 // linearization-dependent per-step data (dsqp_solver.cc:670-718, 893-948, 1116-1123)
 __device__ __forceinline__ void assemble_rows(Ctx &c, const csdo_params &P) {
-  const int NT = c.NT, Nt = c.Nt, t = c.t;
-  if (c.active) {
-    const double yaw0 = c.cur[2 * NT + t], st0 = c.cur[3 * NT + t], v0 = c.cur[4 * NT + t];
+  const int NT = c.NT(), Nt = c.Nt(), t = c.t();
+  if (c.active()) {
+    const double yaw0 = c.cur()[2 * NT + t], st0 = c.cur()[3 * NT + t], v0 = c.cur()[4 * NT + t];
     const double sn = sin(yaw0), cs = cos(yaw0);
-    c.ros[RO_SN * NT + c.t] = sn;
-    c.ros[RO_CS * NT + c.t] = cs;
-    if (c.has_next) {
+    c.ros()[RO_SN * NT + c.t()] = sn;
+    c.ros()[RO_CS * NT + c.t()] = cs;
+    if (c.has_next()) {
       const double cd = cos(st0);
-      c.ros[RO_A1 * NT + c.t] = -P.dt * (v0 * sn);
-      c.ros[RO_A2 * NT + c.t] = P.dt * (v0 * cs);
-      c.ros[RO_A3 * NT + c.t] = (P.dt / P.WB * v0) / (cd * cd);
-      c.ros[RO_B3 * NT + c.t] = P.dt / P.WB * tan(st0);
-      c.ros[RO_KR0 * NT + c.t] = -(P.dt * yaw0 * v0 * sn);
-      c.ros[RO_KR1 * NT + c.t] = -(-P.dt * yaw0 * v0 * cs);
-      c.ros[RO_KR2 * NT + c.t] = -(-P.dt * (st0 * v0 / P.WB / (cd * cd)));
+      c.ros()[RO_A1 * NT + c.t()] = -P.dt * (v0 * sn);
+      c.ros()[RO_A2 * NT + c.t()] = P.dt * (v0 * cs);
+      c.ros()[RO_A3 * NT + c.t()] = (P.dt / P.WB * v0) / (cd * cd);
+      c.ros()[RO_B3 * NT + c.t()] = P.dt / P.WB * tan(st0);
+      c.ros()[RO_KR0 * NT + c.t()] = -(P.dt * yaw0 * v0 * sn);
+      c.ros()[RO_KR1 * NT + c.t()] = -(-P.dt * yaw0 * v0 * cs);
+      c.ros()[RO_KR2 * NT + c.t()] = -(-P.dt * (st0 * v0 / P.WB / (cd * cd)));
     }
     const double dxf = -P.f2x * sn, dyf = P.f2x * cs, dxr = -P.r2x * sn, dyr = P.r2x * cs;
     const double exf = P.f2x * (cs + yaw0 * sn), eyf = P.f2x * (sn - yaw0 * cs);
     const double exr = P.r2x * (cs + yaw0 * sn), eyr = P.r2x * (sn - yaw0 * cs);
-    c.ros[RO_CL0 * NT + c.t] = c.corr[0 * Nt + t] - exf; c.ros[RO_CU0 * NT + c.t] = c.corr[1 * Nt + t] - exf;
-    c.ros[RO_CL1 * NT + c.t] = c.corr[2 * Nt + t] - eyf; c.ros[RO_CU1 * NT + c.t] = c.corr[3 * Nt + t] - eyf;
-    c.ros[RO_CL2 * NT + c.t] = c.corr[4 * Nt + t] - exr; c.ros[RO_CU2 * NT + c.t] = c.corr[5 * Nt + t] - exr;
-    c.ros[RO_CL3 * NT + c.t] = c.corr[6 * Nt + t] - eyr; c.ros[RO_CU3 * NT + c.t] = c.corr[7 * Nt + t] - eyr;
-    for (int k = c.pstart[t]; k < c.pstart[t + 1]; ++k) {
-      const double *pl = c.plane_abc + (size_t)12 * k;
+    c.ros()[RO_CL0 * NT + c.t()] = c.corr()[0 * Nt + t] - exf; c.ros()[RO_CU0 * NT + c.t()] = c.corr()[1 * Nt + t] - exf;
+    c.ros()[RO_CL1 * NT + c.t()] = c.corr()[2 * Nt + t] - eyf; c.ros()[RO_CU1 * NT + c.t()] = c.corr()[3 * Nt + t] - eyf;
+    c.ros()[RO_CL2 * NT + c.t()] = c.corr()[4 * Nt + t] - exr; c.ros()[RO_CU2 * NT + c.t()] = c.corr()[5 * Nt + t] - exr;
+    c.ros()[RO_CL3 * NT + c.t()] = c.corr()[6 * Nt + t] - eyr; c.ros()[RO_CU3 * NT + c.t()] = c.corr()[7 * Nt + t] - eyr;
+    for (int k = c.pstart()[t]; k < c.pstart()[t + 1]; ++k) {
+      const double *pl = c.plane_abc() + (size_t)12 * k;
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const double a = pl[3 * r], b = pl[3 * r + 1], cc = pl[3 * r + 2];
         const double dx = r < 2 ? dxf : dxr, dy = r < 2 ? dyf : dyr;
         const double ex = r < 2 ? exf : exr, ey = r < 2 ? eyf : eyr;
-        double *q = c.pl + (size_t)PL_COUNT * (4 * k + r);
+        double *q = c.pl() + (size_t)PL_COUNT * (4 * k + r);
         q[PL_A] = a * 1.0;
         q[PL_B] = b * 1.0;
         q[PL_G] = a * dx + b * dy;
@@ -381,44 +392,44 @@ __device__ __forceinline__ void assemble_rows(Ctx &c, const csdo_params &P) {
 
 // OSQP scale_data, `scaling` Ruiz passes; leaves D, E, c
 __device__ __forceinline__ void ruiz_scale(Ctx &c, const csdo_params &P) {
-  const int NT = c.NT, t = c.t, Nt = c.Nt;
-  if (c.active) {
+  const int NT = c.NT(), t = c.t(), Nt = c.Nt();
+  if (c.active()) {
     ResetF rf;
     visit_rows(c, P, rf);
 #pragma unroll
-    for (int k = 0; k < 6; ++k) c.D[k * NT + t] = 1.0;
+    for (int k = 0; k < 6; ++k) c.D()[k * NT + t] = 1.0;
   }
   c.c = 1.0;
   __syncthreads();
   for (int pass = 0; pass < P.scaling; ++pass) {
     double dt_new[6];
-    if (c.active) {
+    if (c.active()) {
       ScaleF sf;
-      load_xv(c, c.D, sf.dv);
+      load_xv(c, c.D(), sf.dv);
 #pragma unroll
       for (int k = 0; k < 10; ++k) sf.cmax[k] = 0.0;
       visit_rows(c, P, sf);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) c.carry[k * NT + t] = sf.cmax[6 + k];
+      for (int k = 0; k < 4; ++k) c.carry()[k * NT + t] = sf.cmax[6 + k];
 #pragma unroll
       for (int k = 0; k < 6; ++k) dt_new[k] = sf.cmax[k];
     }
     __syncthreads();
-    if (c.active) {
+    if (c.active()) {
       const int nv = nvar(c);
 #pragma unroll
       for (int k = 0; k < 6; ++k) {
         if (k >= nv) continue;
-        const double dk = c.D[k * NT + t];
+        const double dk = c.D()[k * NT + t];
         double a = dt_new[k];
-        if (k < 4 && t > 0) a = fmax(a, c.carry[k * NT + t - 1]);
+        if (k < 4 && t > 0) a = fmax(a, c.carry()[k * NT + t - 1]);
         double colA = a * dk;  // inf-norm of column k of the scaled A
         double colP = 0.0;     // inf-norm of the column of the scaled (symmetric) P
         if (k == VV) {
           const double pv = (t != 0 && t != Nt - 2) ? 2.0 : 1.0;
           colP = pv * dk;
-          if (t > 0) colP = fmax(colP, c.D[VV * NT + t - 1]);
-          if (t < Nt - 2) colP = fmax(colP, c.D[VV * NT + t + 1]);
+          if (t > 0) colP = fmax(colP, c.D()[VV * NT + t - 1]);
+          if (t < Nt - 2) colP = fmax(colP, c.D()[VV * NT + t + 1]);
           colP = c.c * dk * colP;
         } else if (k == VW) {
           colP = c.c * dk * dk;
@@ -427,24 +438,24 @@ __device__ __forceinline__ void ruiz_scale(Ctx &c, const csdo_params &P) {
       }
     }
     __syncthreads();
-    if (c.active) {
+    if (c.active()) {
       const int nv = nvar(c);
 #pragma unroll
       for (int k = 0; k < 6; ++k)
-        if (k < nv) c.D[k * NT + t] *= dt_new[k];
+        if (k < nv) c.D()[k * NT + t] *= dt_new[k];
     }
     __syncthreads();
     // cost normalisation: mean column norm of the new P (q = 0 -> its norm counts as 1)
     double s[1] = {0.0};
-    if (c.active && c.has_next) {
-      const double dvv = c.D[VV * NT + t], dw = c.D[VW * NT + t];
+    if (c.active() && c.has_next()) {
+      const double dvv = c.D()[VV * NT + t], dw = c.D()[VW * NT + t];
       const double pv = (t != 0 && t != Nt - 2) ? 2.0 : 1.0;
       double colP = pv * dvv;
-      if (t > 0) colP = fmax(colP, c.D[VV * NT + t - 1]);
-      if (t < Nt - 2) colP = fmax(colP, c.D[VV * NT + t + 1]);
+      if (t > 0) colP = fmax(colP, c.D()[VV * NT + t - 1]);
+      if (t < Nt - 2) colP = fmax(colP, c.D()[VV * NT + t + 1]);
       s[0] = c.c * dvv * colP + c.c * dw * dw;
     }
-    block_reduce<1, false>(s, c.red);
+    block_reduce<1, false>(s, c.red());
     double c_temp = s[0] / (double)(6 * Nt - 2);
     const double inf_norm_q = 1.0;  // limit_scaling(0) == 1
     c_temp = fmax(c_temp, inf_norm_q);
@@ -456,9 +467,9 @@ __device__ __forceinline__ void ruiz_scale(Ctx &c, const csdo_params &P) {
 // reduced KKT  H = c D P D + sigma I + D A_raw' diag(rho E^2) A_raw D  into the
 // band storage, then LDL'.
 __device__ __forceinline__ void form_and_factor(Ctx &c, const csdo_params &P) {
-  const int NT = c.NT, t = c.t, Nt = c.Nt;
+  const int NT = c.NT(), t = c.t(), Nt = c.Nt();
   HasmF hf;
-  if (c.active) {
+  if (c.active()) {
 #pragma unroll
     for (int i = 0; i < 6; ++i)
 #pragma unroll
@@ -472,47 +483,51 @@ __device__ __forceinline__ void form_and_factor(Ctx &c, const csdo_params &P) {
     hf.rho = c.rho;
     visit_rows(c, P, hf);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) c.carry[k * NT + t] = hf.nd[k];
+    for (int k = 0; k < 4; ++k) c.carry()[k * NT + t] = hf.nd[k];
     // clear this step's band rows; the last step's missing v, w are dummy unknowns (H_ii = 1)
+    const int sk0 = make_parts(Nt).skew_of_block(t);
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
 #pragma unroll
-      for (int d = 0; d < 6; ++d) c.bm.L6[(size_t)(6 * t + k) * 6 + d] = 0.0;
-      c.bm.dinv[6 * t + k] = 1.0;
+      for (int d = 0; d < 6; ++d) c.bm().L6[sk0 + (size_t)(6 * t + k) * 6 + d] = 0.0;
+      c.bm().dinv[6 * t + k] = 1.0;
     }
   }
   __syncthreads();
-  if (c.active) {
+  if (c.active()) {
     const int nv = nvar(c);
+    const Parts pt_ = make_parts(Nt);
     double dk[10];
-    load_xv(c, c.D, dk);
+    load_xv(c, c.D(), dk);
     // objective (dsqp_solver.cc:163-197): second difference on v, identity on w
-    if (c.has_next) {
+    if (c.has_next()) {
       hf.q[VV][VV] += c.c * ((t != 0 && t != Nt - 2) ? 2.0 : 1.0);
       hf.q[VW][VW] += c.c * 1.0;
     }
     for (int k = 0; k < nv; ++k) {
-      double *Lr = c.bm.L6 + (size_t)(6 * t + k) * 6 - 1;  // Lr[d] = H_{i,i-d}
+      double *Lr = c.bm().L6 + pt_.skew_of_block(t) + (size_t)(6 * t + k) * 6 - 1;  // Lr[d] = H_{i,i-d}
       double diag = hf.q[k][k];
-      if (k < 4 && t > 0) diag += c.carry[k * NT + t - 1];
-      c.bm.dinv[6 * t + k] = dk[k] * dk[k] * diag + P.sigma;
+      if (k < 4 && t > 0) diag += c.carry()[k * NT + t - 1];
+      c.bm().dinv[6 * t + k] = dk[k] * dk[k] * diag + P.sigma;
       for (int j = 0; j < k; ++j) Lr[k - j] = dk[k] * dk[j] * hf.q[k][j];
     }
-    if (c.has_next) {
+    if (c.has_next()) {
       const int nvn = (t + 1 < Nt - 1) ? 6 : 4;
       for (int k = 0; k < 4; ++k) {  // rows x,y,yaw,steer of step t+1
-        double *Lr = c.bm.L6 + (size_t)(6 * (t + 1) + k) * 6 - 1;
+        double *Lr = c.bm().L6 + pt_.skew_of_block(t + 1) + (size_t)(6 * (t + 1) + k) * 6 - 1;
         for (int j = k; j < 6; ++j) Lr[6 + k - j] = dk[6 + k] * dk[j] * hf.cr[k][j];
       }
       if (nvn == 6) {  // v_{t+1} - v_t coupling of the objective
-        double *Lr = c.bm.L6 + (size_t)(6 * (t + 1) + VV) * 6 - 1;
-        Lr[6] = c.D[VV * NT + t + 1] * dk[VV] * (-c.c);
+        double *Lr = c.bm().L6 + pt_.skew_of_block(t + 1) + (size_t)(6 * (t + 1) + VV) * 6 - 1;
+        Lr[6] = c.D()[VV * NT + t + 1] * dk[VV] * (-c.c);
       }
     }
   }
   __syncthreads();
-  if ((c.tid >> 5) == c.solver_warp) {
-    if (c.l_shared) band_factor_warp<true>(c.bm, Nt); else band_factor_warp<false>(c.bm, Nt);
+  __syncwarp();
+  if ((c.tid() >> 5) == c.solver_warp()) {
+    BandFactorFn fn = *(volatile BandFactorFn *)&g_band_factor[c.l_shared() ? 1 : 0];
+    fn(c.bm(), Nt);
   }
   __syncthreads();
 }
@@ -527,15 +542,15 @@ struct QpOut {
 
 // rhs <- sigma x + D (acc + carry[t-1])   (q = 0)
 __device__ __forceinline__ void finish_rhs(const Ctx &c, const csdo_params &P, const double (&acc)[10]) {
-  const int NT = c.NT, t = c.t;
-  if (c.active) {
+  const int NT = c.NT(), t = c.t();
+  if (c.active()) {
     const int nv = nvar(c);
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
-      if (k >= nv) { c.rhs[k * NT + t] = 0.0; continue; }  // dummy unknowns stay 0
+      if (k >= nv) { c.rhs()[k * NT + t] = 0.0; continue; }  // dummy unknowns stay 0
       double a = acc[k];
-      if (k < 4 && t > 0) a += c.carry[k * NT + t - 1];
-      c.rhs[k * NT + t] = P.sigma * c.x[k * NT + t] + c.D[k * NT + t] * a;
+      if (k < 4 && t > 0) a += c.carry()[k * NT + t - 1];
+      c.rhs()[k * NT + t] = P.sigma * c.x()[k * NT + t] + c.D()[k * NT + t] * a;
     }
   }
 }
@@ -543,15 +558,15 @@ __device__ __forceinline__ void finish_rhs(const Ctx &c, const csdo_params &P, c
 template <int MODE>
 __device__ __forceinline__ void step_rows(Ctx &c, const csdo_params &P, bool store_dy, double rho_old) {
   StepF<MODE> sf;
-  if (c.active) {
-    load_xv(c, c.xt, sf.xv);
+  if (c.active()) {
+    load_xv(c, c.xt(), sf.xv);
 #pragma unroll
     for (int k = 0; k < 10; ++k) sf.acc[k] = 0.0;
     sf.alpha = P.alpha; sf.rho = c.rho; sf.rho_old = rho_old;
-    sf.store_dy = store_dy; sf.dy_base = c.dy + c.t; sf.dy_stride = c.NT;
+    sf.store_dy = store_dy; sf.dy_base = c.dy() + c.t(); sf.dy_stride = c.NT();
     visit_rows(c, P, sf);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) c.carry[k * c.NT + c.t] = sf.acc[6 + k];
+    for (int k = 0; k < 4; ++k) c.carry()[k * c.NT() + c.t()] = sf.acc[6 + k];
   }
   __syncthreads();
   finish_rhs(c, P, sf.acc);
@@ -565,48 +580,48 @@ struct CheckOut {
 };
 
 __device__ __forceinline__ void check_rows(Ctx &c, const csdo_params &P, bool with_dy, CheckOut &co) {
-  const int NT = c.NT, t = c.t, Nt = c.Nt;
+  const int NT = c.NT(), t = c.t(), Nt = c.Nt();
   // xt <- D x (the current iterate, not x~)
-  if (c.active) {
+  if (c.active()) {
 #pragma unroll
-    for (int k = 0; k < 6; ++k) c.xt[k * NT + t] = c.D[k * NT + t] * c.x[k * NT + t];
+    for (int k = 0; k < 6; ++k) c.xt()[k * NT + t] = c.D()[k * NT + t] * c.x()[k * NT + t];
   }
   __syncthreads();
   CheckF cf;
 #pragma unroll
   for (int k = 0; k < N_COUNT; ++k) cf.nrm[k] = 0.0;
   cf.ineq_lhs = 0.0;
-  if (c.active) {
-    load_xv(c, c.xt, cf.xv);
+  if (c.active()) {
+    load_xv(c, c.xt(), cf.xv);
 #pragma unroll
     for (int k = 0; k < 10; ++k) { cf.acc[k] = 0.0; cf.accd[k] = 0.0; }
-    cf.rho = c.rho; cf.with_dy = with_dy; cf.dy_base = c.dy + c.t; cf.dy_stride = c.NT;
+    cf.rho = c.rho; cf.with_dy = with_dy; cf.dy_base = c.dy() + c.t(); cf.dy_stride = c.NT();
     visit_rows(c, P, cf);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      c.carry[k * NT + t] = cf.acc[6 + k];
-      c.rhs[k * NT + t] = cf.accd[6 + k];  // rhs is rebuilt below, see caller
+      c.carry()[k * NT + t] = cf.acc[6 + k];
+      c.rhs()[k * NT + t] = cf.accd[6 + k];  // rhs is rebuilt below, see caller
     }
   }
   __syncthreads();
-  if (c.active) {
+  if (c.active()) {
     const int nv = nvar(c);
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
       if (k >= nv) continue;
-      const double dk = c.D[k * NT + t], dinv = 1.0 / dk;
+      const double dk = c.D()[k * NT + t], dinv = 1.0 / dk;
       double a = cf.acc[k], ad = cf.accd[k];
-      if (k < 4 && t > 0) { a += c.carry[k * NT + t - 1]; ad += c.rhs[k * NT + t - 1]; }
+      if (k < 4 && t > 0) { a += c.carry()[k * NT + t - 1]; ad += c.rhs()[k * NT + t - 1]; }
       const double aty = dk * a;
       double px = 0.0;
       if (k == VV) {
         const double pv = (t != 0 && t != Nt - 2) ? 2.0 : 1.0;
-        double sacc = pv * (dk * c.x[VV * NT + t]);
-        if (t > 0) sacc -= c.D[VV * NT + t - 1] * c.x[VV * NT + t - 1];
-        if (t < Nt - 2) sacc -= c.D[VV * NT + t + 1] * c.x[VV * NT + t + 1];
+        double sacc = pv * (dk * c.x()[VV * NT + t]);
+        if (t > 0) sacc -= c.D()[VV * NT + t - 1] * c.x()[VV * NT + t - 1];
+        if (t < Nt - 2) sacc -= c.D()[VV * NT + t + 1] * c.x()[VV * NT + t + 1];
         px = c.c * dk * sacc;
       } else if (k == VW) {
-        px = c.c * dk * (dk * c.x[VW * NT + t]);
+        px = c.c * dk * (dk * c.x()[VW * NT + t]);
       }
       const double r = px + aty;
       cf.nrm[N_DUA_S] = fmax(cf.nrm[N_DUA_S], fabs(r));
@@ -619,9 +634,9 @@ __device__ __forceinline__ void check_rows(Ctx &c, const csdo_params &P, bool wi
     }
   }
   __syncthreads();
-  block_reduce<N_COUNT, true>(cf.nrm, c.red);
+  block_reduce<N_COUNT, true>(cf.nrm, c.red());
   double s[1] = {cf.ineq_lhs};
-  block_reduce<1, false>(s, c.red);
+  block_reduce<1, false>(s, c.red());
 #pragma unroll
   for (int k = 0; k < N_COUNT; ++k) co.nrm[k] = cf.nrm[k];
   co.ineq_lhs = s[0];
@@ -637,7 +652,7 @@ __device__ int termination_status(const Ctx &c, const csdo_params &P, const Chec
   const double eps_prim = eps_abs + eps_rel * fmax(co.nrm[N_Z_U], co.nrm[N_AX_U]);
   bool prim_ok = false, prim_inf = false;
   if (pri_res < eps_prim) prim_ok = true;
-  else if (c.K == 0) {
+  else if (c.K() == 0) {
     // is_primal_infeasible; with K > 0 every inter-vehicle row carries a true
     // -inf lower bound and the support-function sum is NaN, so the test never fires
     const double ndy = co.nrm[N_DY];
@@ -650,9 +665,9 @@ __device__ int termination_status(const Ctx &c, const csdo_params &P, const Chec
   return 0;
 }
 
-// solveOSQP (dsqp_solver.cc:423-555): setup + warm start + ADMM; solution in c.sol
+// solveOSQP (dsqp_solver.cc:423-555): setup + warm start + ADMM; solution in c.sol()
 __device__ __forceinline__ QpOut solve_qp(Ctx &c, const csdo_params &P) {
-  const int NT = c.NT, t = c.t, Nt = c.Nt;
+  const int NT = c.NT(), t = c.t(), Nt = c.Nt();
   QpOut out{CSDO_QP_UNSOLVED, 0, 1};
   PH_T0();
   ruiz_scale(c, P);
@@ -661,37 +676,43 @@ __device__ __forceinline__ QpOut solve_qp(Ctx &c, const csdo_params &P) {
   form_and_factor(c, P);
   PH_ADD(3);
   // osqp_warm_start_x: x <- Dinv x0, z <- A x, y = 0
-  if (c.active) {
+  if (c.active()) {
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
-      const double dk = c.D[k * NT + t];
-      const double xs = c.cur[k * NT + t] * (1.0 / dk);
-      c.x[k * NT + t] = xs;
-      c.xt[k * NT + t] = dk * xs;
+      const double dk = c.D()[k * NT + t];
+      const double xs = c.cur()[k * NT + t] * (1.0 / dk);
+      c.x()[k * NT + t] = xs;
+      c.xt()[k * NT + t] = dk * xs;
     }
   }
   __syncthreads();
   step_rows<0>(c, P, false, 0.0);
-  const bool keep_dy = (c.K == 0);
+  const bool keep_dy = (c.K() == 0);
   CheckOut co;
   bool checked = false;
   int iter = 0;
   PH_ADD(5);
   for (iter = 1; iter <= P.osqp_max_iter; ++iter) {
-    if ((c.tid >> 5) == c.solver_warp) {
-      if (c.l_shared) band_solve_warp<true>(c.bm, c.rhs, c.xt, Nt, NT);
-      else band_solve_warp<false>(c.bm, c.rhs, c.xt, Nt, NT);
+    __syncwarp();  // the solver warp must enter the solve converged (threads leave barriers individually)
+    if ((c.tid() >> 5) == c.solver_warp()) {
+      BandSolveFn fn = *(volatile BandSolveFn *)&g_band_solve[c.l_shared() ? 1 : 0];
+      fn(c.bm(), c.rhs(), c.xt(), Nt, NT);
+#ifdef CSDO_DOUBLE_SOLVE  // timing experiment: a second, discarded solve right after the first (warm instruction cache)
+      PH_ADD(4);
+      band_solve_warp<true>(c.bm(), c.xt(), c.xt(), Nt, NT);
+      PH_ADD(7);
+#endif
     }
     __syncthreads();
     PH_ADD(4);
-    if (c.active) {
+    if (c.active()) {
       const int nv = nvar(c);
 #pragma unroll
       for (int k = 0; k < 6; ++k) {
         if (k >= nv) continue;
-        const double xtil = c.rhs[k * NT + t], xp = c.x[k * NT + t];
-        c.x[k * NT + t] = P.alpha * xtil + (1.0 - P.alpha) * xp;
-        c.xt[k * NT + t] = c.D[k * NT + t] * xtil;
+        const double xtil = c.rhs()[k * NT + t], xp = c.x()[k * NT + t];
+        c.x()[k * NT + t] = P.alpha * xtil + (1.0 - P.alpha) * xp;
+        c.xt()[k * NT + t] = c.D()[k * NT + t] * xtil;
       }
     }
     __syncthreads();
@@ -705,15 +726,15 @@ __device__ __forceinline__ QpOut solve_qp(Ctx &c, const csdo_params &P) {
     if (can_check || adapt) {
       // check_rows borrows rhs/carry as scratch: save the next right-hand side in xt afterwards
       double keep[6];
-      if (c.active)
+      if (c.active())
 #pragma unroll
-        for (int k = 0; k < 6; ++k) keep[k] = c.rhs[k * NT + t];
+        for (int k = 0; k < 6; ++k) keep[k] = c.rhs()[k * NT + t];
       __syncthreads();
       check_rows(c, P, keep_dy && store_dy, co);
       PH_ADD(6);
-      if (c.active)
+      if (c.active())
 #pragma unroll
-        for (int k = 0; k < 6; ++k) c.rhs[k * NT + t] = keep[k];
+        for (int k = 0; k < 6; ++k) c.rhs()[k * NT + t] = keep[k];
       __syncthreads();
       checked = can_check;
       if (can_check) {
@@ -744,14 +765,14 @@ __device__ __forceinline__ QpOut solve_qp(Ctx &c, const csdo_params &P) {
   if (out.status == CSDO_QP_UNSOLVED) {
     if (!checked) {
       double keep[6];
-      if (c.active)
+      if (c.active())
 #pragma unroll
-        for (int k = 0; k < 6; ++k) keep[k] = c.rhs[k * NT + t];
+        for (int k = 0; k < 6; ++k) keep[k] = c.rhs()[k * NT + t];
       __syncthreads();
       check_rows(c, P, keep_dy, co);
-      if (c.active)
+      if (c.active())
 #pragma unroll
-        for (int k = 0; k < 6; ++k) c.rhs[k * NT + t] = keep[k];
+        for (int k = 0; k < 6; ++k) c.rhs()[k * NT + t] = keep[k];
       __syncthreads();
       const int st = termination_status(c, P, co, false);
       if (st != 0) out.status = st;
@@ -765,43 +786,43 @@ __device__ __forceinline__ QpOut solve_qp(Ctx &c, const csdo_params &P) {
   const bool has_solution = !(out.status == CSDO_QP_PRIMAL_INFEASIBLE ||
                               out.status == CSDO_QP_PRIMAL_INFEASIBLE_INACCURATE ||
                               out.status == CSDO_QP_NON_CVX);
-  if (c.active) {
+  if (c.active()) {
     const int nv = nvar(c);
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
       double v = 0.0;
-      if (k < nv) v = (has_solution && abs(out.status) <= 2) ? c.D[k * NT + t] * c.x[k * NT + t] : c.cur[k * NT + t];
-      c.sol[k * NT + t] = v;
+      if (k < nv) v = (has_solution && abs(out.status) <= 2) ? c.D()[k * NT + t] * c.x()[k * NT + t] : c.cur()[k * NT + t];
+      c.sol()[k * NT + t] = v;
     }
   }
   __syncthreads();
   return out;
 }
 
-// isFeasible (dsqp_solver.cc:292-420), fully_check = false, on c.sol
+// isFeasible (dsqp_solver.cc:292-420), fully_check = false, on c.sol()
 __device__ __forceinline__ bool is_feasible(Ctx &c, const csdo_params &P) {
-  const int NT = c.NT, t = c.t, Nt = c.Nt;
+  const int NT = c.NT(), t = c.t(), Nt = c.Nt();
   double s[1] = {0.0};
   double mx[2] = {0.0, 0.0};
-  if (c.active) {
-    const double x0 = c.sol[0 * NT + t], y0 = c.sol[1 * NT + t], yaw0 = c.sol[2 * NT + t];
+  if (c.active()) {
+    const double x0 = c.sol()[0 * NT + t], y0 = c.sol()[1 * NT + t], yaw0 = c.sol()[2 * NT + t];
     const double cs = cos(yaw0), sn = sin(yaw0);
-    if (c.has_next) {
-      const double st0 = c.sol[3 * NT + t], v0 = c.sol[4 * NT + t], w0 = c.sol[5 * NT + t];
-      double a = x0 + v0 * cs * P.dt - c.sol[0 * NT + t + 1]; s[0] += a * a;
-      a = y0 + v0 * sn * P.dt - c.sol[1 * NT + t + 1]; s[0] += a * a;
-      a = yaw0 + v0 * tan(st0) / P.WB * P.dt - c.sol[2 * NT + t + 1]; s[0] += a * a;
-      a = st0 + w0 * P.dt - c.sol[3 * NT + t + 1]; s[0] += a * a;
+    if (c.has_next()) {
+      const double st0 = c.sol()[3 * NT + t], v0 = c.sol()[4 * NT + t], w0 = c.sol()[5 * NT + t];
+      double a = x0 + v0 * cs * P.dt - c.sol()[0 * NT + t + 1]; s[0] += a * a;
+      a = y0 + v0 * sn * P.dt - c.sol()[1 * NT + t + 1]; s[0] += a * a;
+      a = yaw0 + v0 * tan(st0) / P.WB * P.dt - c.sol()[2 * NT + t + 1]; s[0] += a * a;
+      a = st0 + w0 * P.dt - c.sol()[3 * NT + t + 1]; s[0] += a * a;
     }
     const double Y[4] = {x0 + P.f2x * cs, y0 + P.f2x * sn, x0 + P.r2x * cs, y0 + P.r2x * sn};
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const double lo = c.corr[(2 * q) * Nt + t], hi = c.corr[(2 * q + 1) * Nt + t];
+      const double lo = c.corr()[(2 * q) * Nt + t], hi = c.corr()[(2 * q + 1) * Nt + t];
       if (!(lo <= Y[q])) mx[0] = fmax(mx[0], lo - Y[q]);
       if (!(Y[q] <= hi)) mx[0] = fmax(mx[0], Y[q] - hi);
     }
-    for (int k = c.pstart[t]; k < c.pstart[t + 1]; ++k) {
-      const double *pl = c.plane_abc + (size_t)12 * k;
+    for (int k = c.pstart()[t]; k < c.pstart()[t + 1]; ++k) {
+      const double *pl = c.plane_abc() + (size_t)12 * k;
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const double res = r < 2 ? pl[3 * r] * Y[0] + pl[3 * r + 1] * Y[1] + pl[3 * r + 2]
@@ -810,8 +831,8 @@ __device__ __forceinline__ bool is_feasible(Ctx &c, const csdo_params &P) {
       }
     }
   }
-  block_reduce<1, false>(s, c.red);
-  block_reduce<2, true>(mx, c.red);
+  block_reduce<1, false>(s, c.red());
+  block_reduce<2, true>(mx, c.red());
   const double err_kin = s[0] / (double)Nt;
   return err_kin < 1e-2 && mx[1] < 1e-1 && mx[0] < 1e-1;
 }
@@ -826,22 +847,26 @@ __device__ __forceinline__ void refine_body(const DevBatch &B, const DevOut &O, 
   extern __shared__ double smem[];
   __shared__ int s_agent;
   __shared__ int s_flag;
+  __shared__ CtxShared cs;
   Ctx c;
-  c.NT = LY.NT; c.KP = 4 * LY.KMAX; c.tid = threadIdx.x; c.nthr = blockDim.x; c.t = threadIdx.x;
-  const int NT = c.NT;
+  c.s = &cs;
+  const int NT = LY.NT;
   double *slot = scratch + (size_t)blockIdx.x * LY.slot_doubles;
-  c.x = smem + LY.o_x; c.xt = smem + LY.o_xt; c.rhs = smem + LY.o_rhs; c.D = smem + LY.o_D;
-  c.carry = smem + LY.o_carry; c.red = smem + LY.o_red;
-  c.ros = smem + LY.o_ro; c.cfgs = c.ros + RO_COUNT * NT; c.Es = smem + LY.o_E; c.ws = smem + LY.o_w;
-  c.pstart = reinterpret_cast<int *>(smem + LY.o_pstart);
-  c.bm.L6 = LY.tier >= 2 ? slot + LY.g_L : smem + LY.o_L;
-  c.bm.dinv = c.bm.L6 + 36 * NT;
-  c.l_shared = LY.tier < 2;
-  c.bm.Sinv = smem + LY.o_sinv;
-  c.bm.sv = c.bm.Sinv + kMaxNs * kMaxNs;
-  c.bm.G = c.xt;  // xt and rhs are contiguous and free while a factorization runs
-  c.cur = slot + LY.g_cur; c.sol = slot + LY.g_sol; c.dy = slot + LY.g_dy;
-  c.pl_glob = slot + LY.g_pl; c.pl_smem = smem + LY.o_pl; c.KS = LY.KS;
+  if (threadIdx.x == 0) {
+    cs.NT = LY.NT; cs.KP = 4 * LY.KMAX;
+    cs.x = smem + LY.o_x; cs.xt = smem + LY.o_xt; cs.rhs = smem + LY.o_rhs; cs.D = smem + LY.o_D;
+    cs.carry = smem + LY.o_carry; cs.red = smem + LY.o_red;
+    cs.ros = smem + LY.o_ro; cs.cfgs = cs.ros + RO_COUNT * NT; cs.Es = smem + LY.o_E; cs.ws = smem + LY.o_w;
+    cs.pstart = reinterpret_cast<int *>(smem + LY.o_pstart);
+    cs.bm.L6 = LY.tier >= 2 ? slot + LY.g_L : smem + LY.o_L;
+    cs.bm.dinv = cs.bm.L6 + 36 * NT + kSkewPad;
+    cs.l_shared = LY.tier < 2;
+    cs.bm.Sinv = smem + LY.o_sinv;
+    cs.bm.sv = cs.bm.Sinv + kMaxNs * kMaxNs;
+    cs.bm.G = cs.xt;  // xt and rhs are contiguous and free while a factorization runs
+    cs.cur = slot + LY.g_cur; cs.sol = slot + LY.g_sol; cs.dy = slot + LY.g_dy;
+    cs.pl_glob = slot + LY.g_pl; cs.pl_smem = smem + LY.o_pl; cs.KS = LY.KS;
+  }
 
   for (int k = 0; k < 8; ++k) c.ph[k] = 0;
   // The warp that runs the band factor/solve differs between the CTAs resident on one SM, so that
@@ -852,7 +877,7 @@ __device__ __forceinline__ void refine_body(const DevBatch &B, const DevOut &O, 
     s_flag = atomicAdd(queue + 32 + (smid & 255), 1);
   }
   __syncthreads();
-  c.solver_warp = s_flag % ((blockDim.x + 31) >> 5);
+  if (threadIdx.x == 0) cs.solver_warp = s_flag % ((blockDim.x + 31) >> 5);
   __syncthreads();
   for (;;) {
     if (threadIdx.x == 0) s_agent = atomicAdd(queue, 1);
@@ -860,7 +885,6 @@ __device__ __forceinline__ void refine_body(const DevBatch &B, const DevOut &O, 
     const int qi = s_agent;
     __syncthreads();
     if (qi >= B.n_agents) break;
-    c.ph[7] -= 0;
     const int a = B.agent_order ? B.agent_order[qi] : qi;
     // instance of this agent: last i with inst_agent_ptr[i] <= a
     int lo = 0, hi = B.n_inst;
@@ -871,47 +895,48 @@ __device__ __forceinline__ void refine_body(const DevBatch &B, const DevOut &O, 
     const int inst = lo;
     const int Nt = B.inst_nt[inst];
     const int64_t off = B.agent_off[a];
-    c.Nt = Nt;
-    c.active = c.t < Nt;
-    c.has_next = c.t < Nt - 1;
-    c.K = B.plane_ptr[a + 1] - B.plane_ptr[a];
-    c.pl = c.K <= c.KS ? c.pl_smem : c.pl_glob;
-    c.plane_t = B.plane_t + B.plane_ptr[a];
-    c.plane_abc = B.plane_abc + (size_t)12 * B.plane_ptr[a];
-    c.No = B.obs_ptr[inst + 1] - B.obs_ptr[inst];
-    c.obs = B.obs + (size_t)3 * B.obs_ptr[inst];
-    c.dimx = B.inst_dims[2 * inst]; c.dimy = B.inst_dims[2 * inst + 1];
-    c.guess = B.guess + 6 * off;
-    c.corr = O.corridors + 8 * off;
+    if (threadIdx.x == 0) {
+      cs.Nt = Nt;
+      cs.K = B.plane_ptr[a + 1] - B.plane_ptr[a];
+      cs.pl = cs.K <= cs.KS ? cs.pl_smem : cs.pl_glob;
+      cs.plane_t = B.plane_t + B.plane_ptr[a];
+      cs.plane_abc = B.plane_abc + (size_t)12 * B.plane_ptr[a];
+      cs.No = B.obs_ptr[inst + 1] - B.obs_ptr[inst];
+      cs.obs = B.obs + (size_t)3 * B.obs_ptr[inst];
+      cs.dimx = B.inst_dims[2 * inst]; cs.dimy = B.inst_dims[2 * inst + 1];
+      cs.guess = B.guess + 6 * off;
+      cs.corr = O.corridors + 8 * off;
+    }
+    __syncthreads();
     double *traj = O.traj + 6 * off;
     // planes of each step: planes are sorted by t (inter_agent_cons.cc:26-31)
-    for (int tt = c.tid; tt <= Nt; tt += c.nthr) {
-      int l2 = 0, h2 = c.K;
-      while (l2 < h2) { const int mid = (l2 + h2) >> 1; if (c.plane_t[mid] < tt) l2 = mid + 1; else h2 = mid; }
-      c.pstart[tt] = l2;
+    for (int tt = c.tid(); tt <= Nt; tt += c.nthr()) {
+      int l2 = 0, h2 = c.K();
+      while (l2 < h2) { const int mid = (l2 + h2) >> 1; if (c.plane_t()[mid] < tt) l2 = mid + 1; else h2 = mid; }
+      c.pstart()[tt] = l2;
     }
     // solution0 and the frozen trust centre (dsqp_solver.cc:56-63); cfg (utils.cc:115-120)
-    if (c.active) {
+    if (c.active()) {
 #pragma unroll
       for (int k = 0; k < 6; ++k) {
-        double v = c.guess[k * Nt + c.t];
-        if (k >= 4 && !c.has_next) v = 0.0;
-        c.cur[k * NT + c.t] = v;
-        c.sol[k * NT + c.t] = v;
+        double v = c.guess()[k * Nt + c.t()];
+        if (k >= 4 && !c.has_next()) v = 0.0;
+        c.cur()[k * NT + c.t()] = v;
+        c.sol()[k * NT + c.t()] = v;
       }
-      c.ros[RO_TRX * NT + c.t] = c.guess[0 * Nt + c.t];
-      c.ros[RO_TRY * NT + c.t] = c.guess[1 * Nt + c.t];
+      c.ros()[RO_TRX * NT + c.t()] = c.guess()[0 * Nt + c.t()];
+      c.ros()[RO_TRY * NT + c.t()] = c.guess()[1 * Nt + c.t()];
     }
     if (threadIdx.x == 0) {
-      c.cfgs[0] = c.guess[0]; c.cfgs[1] = c.guess[Nt - 1];
-      c.cfgs[2] = c.guess[Nt]; c.cfgs[3] = c.guess[2 * Nt - 1];
-      c.cfgs[4] = c.guess[2 * Nt]; c.cfgs[5] = c.guess[3 * Nt - 1];
+      c.cfgs()[0] = c.guess()[0]; c.cfgs()[1] = c.guess()[Nt - 1];
+      c.cfgs()[2] = c.guess()[Nt]; c.cfgs()[3] = c.guess()[2 * Nt - 1];
+      c.cfgs()[4] = c.guess()[2 * Nt]; c.cfgs()[5] = c.guess()[3 * Nt - 1];
     }
     if (threadIdx.x == 0) s_flag = 0;
     __syncthreads();
     // calcCorridors (dsqp_solver.cc:1154) on float disc centres
     PH_T0();
-    if (agent_corridors(c, P, c.guess, c.guess + Nt, c.guess + 2 * Nt, 1, false, nullptr)) s_flag = 1;
+    if (agent_corridors(c, P, c.guess(), c.guess() + Nt, c.guess() + 2 * Nt, 1, false, nullptr)) s_flag = 1;
     __syncthreads();
     if (threadIdx.x == 0 && s_flag) atomicAnd(&O.inst_static_legal[inst], 0);
     __syncthreads();
@@ -928,42 +953,42 @@ __device__ __forceinline__ void refine_body(const DevBatch &B, const DevOut &O, 
       ph_t0 = clock64();
       status = q.status; admm += q.iters; nfac += q.n_factor;
       double s[1] = {0.0};
-      if (c.active) {
+      if (c.active()) {
         const int nv = nvar(c);
 #pragma unroll
         for (int k = 0; k < 6; ++k)
-          if (k < nv) { const double d = c.sol[k * NT + c.t] - c.cur[k * NT + c.t]; s[0] += d * d; }
+          if (k < nv) { const double d = c.sol()[k * NT + c.t()] - c.cur()[k * NT + c.t()]; s[0] += d * d; }
       }
-      block_reduce<1, false>(s, c.red);
+      block_reduce<1, false>(s, c.red());
       delta = s[0];
       iter_count++;
       if (iter_count > P.max_iter / 2 && is_feasible(c, P)) break;
-      if (c.active)
+      if (c.active())
 #pragma unroll
-        for (int k = 0; k < 6; ++k) c.cur[k * NT + c.t] = c.sol[k * NT + c.t];
+        for (int k = 0; k < 6; ++k) c.cur()[k * NT + c.t()] = c.sol()[k * NT + c.t()];
       __syncthreads();
       if (!P.fixed_corridor) {
         PH_ADD(7);
-        agent_corridors(c, P, c.sol, c.sol + NT, c.sol + 2 * NT, 0, true, nullptr);
+        agent_corridors(c, P, c.sol(), c.sol() + NT, c.sol() + 2 * NT, 0, true, nullptr);
         __syncthreads();
         PH_ADD(0);
       }
     }
     // extractSingleSolutionVec2OptRes + per-agent records
     double ob[1] = {0.0};
-    if (c.active) {
+    if (c.active()) {
 #pragma unroll
-      for (int k = 0; k < 6; ++k) traj[k * Nt + c.t] = c.sol[k * NT + c.t];
-      if (c.has_next) {
-        const double w0 = c.sol[5 * NT + c.t];
+      for (int k = 0; k < 6; ++k) traj[k * Nt + c.t()] = c.sol()[k * NT + c.t()];
+      if (c.has_next()) {
+        const double w0 = c.sol()[5 * NT + c.t()];
         ob[0] = 0.5 * w0 * w0;
-        if (c.t + 1 < Nt - 1) {
-          const double dv = c.sol[4 * NT + c.t + 1] - c.sol[4 * NT + c.t];
+        if (c.t() + 1 < Nt - 1) {
+          const double dv = c.sol()[4 * NT + c.t() + 1] - c.sol()[4 * NT + c.t()];
           ob[0] += 0.5 * dv * dv;
         }
       }
     }
-    block_reduce<1, false>(ob, c.red);
+    block_reduce<1, false>(ob, c.red());
     if (threadIdx.x == 0) {
       O.status[a] = status; O.sqp_iters[a] = iter_count; O.n_qp[a] = iter_count;
       O.admm_iters[a] = admm; O.n_factor[a] = nfac; O.objective[a] = ob[0];
@@ -971,7 +996,7 @@ __device__ __forceinline__ void refine_body(const DevBatch &B, const DevOut &O, 
     __syncthreads();
     PH_ADD(7);
   }
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 32 * c.solver_warp()) {  // lane 0 of the solver warp: it works in every phase
     unsigned long long *prof = reinterpret_cast<unsigned long long *>(queue + 2);
     for (int k = 0; k < 8; ++k) atomicAdd(prof + k, (unsigned long long)c.ph[k]);
   }
@@ -1020,12 +1045,16 @@ __global__ void corridors_kernel(const DevBatch B, const csdo_params P, int doub
   while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (B.inst_agent_ptr[mid] <= a) lo = mid; else hi = mid; }
   const int inst = lo, Nt = B.inst_nt[inst];
   const int64_t off = B.agent_off[a];
+  __shared__ CtxShared cs;
   Ctx c;
-  c.Nt = Nt; c.tid = threadIdx.x; c.nthr = blockDim.x;
-  c.No = B.obs_ptr[inst + 1] - B.obs_ptr[inst];
-  c.obs = B.obs + (size_t)3 * B.obs_ptr[inst];
-  c.dimx = B.inst_dims[2 * inst]; c.dimy = B.inst_dims[2 * inst + 1];
-  c.corr = corridors + 8 * off;
+  c.s = &cs;
+  if (threadIdx.x == 0) {
+    cs.Nt = Nt;
+    cs.No = B.obs_ptr[inst + 1] - B.obs_ptr[inst];
+    cs.obs = B.obs + (size_t)3 * B.obs_ptr[inst];
+    cs.dimx = B.inst_dims[2 * inst]; cs.dimy = B.inst_dims[2 * inst + 1];
+    cs.corr = corridors + 8 * off;
+  }
   const double *g = B.guess + 6 * off;
   if (threadIdx.x == 0) s_flag = 0;
   __syncthreads();
@@ -1051,15 +1080,15 @@ Layout make_layout(int NT, int KMAX, int tier, int KS) {
   l.o_w = take(16 * NT);
   l.o_red = take(((NT + 31) / 32 + 1) * N_COUNT);
   l.o_pstart = take((NT + 2 + 1) / 2);
-  l.o_sinv = take(kMaxNs * kMaxNs + 3 * kMaxNs);
-  l.o_L = tier < 2 ? take(kLw * 6 * NT) : 0;
+  l.o_sinv = take(kMaxNs * kMaxNs + 3 * kMaxNs + 8);
+  l.o_L = tier < 2 ? take(kLw * 6 * NT + kSkewPad) : 0;
   l.o_pl = take(PL_COUNT * 4 * KS);
   l.smem_doubles = o;
   size_t g = 0;
   auto gtake = [&](size_t n) { size_t r = g; g += (n + 1) & ~(size_t)1; return r; };
   l.g_cur = gtake(6 * (size_t)NT); l.g_sol = gtake(6 * (size_t)NT); l.g_dy = gtake(16 * (size_t)NT);
   l.g_pl = gtake((size_t)PL_COUNT * 4 * KMAX);
-  l.g_L = gtake((size_t)kLw * 6 * NT);
+  l.g_L = gtake((size_t)kLw * 6 * NT + kSkewPad);
   l.slot_doubles = g;
   return l;
 }
@@ -1070,6 +1099,8 @@ cudaError_t launch_refine(const DevBatch &B, const DevOut &O, const csdo_params 
   RefineKernel kern = pick_kernel(block);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
+  if (const char *co = getenv("CSDO_CARVEOUT"))  // developer knob: shared-memory carve-out in percent
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(co));
   e = cudaMemsetAsync(queue, 0, 2048, stream);
   if (e != cudaSuccess) return e;
   const int fb = 256;

@@ -11,9 +11,11 @@ __global__ void k(long long *cyc, double *sink, int Nt, int NT, int reps, int nl
   __syncthreads();
   const int lane = threadIdx.x;
   const int per = Nt / nlanes;
+  const Parts pt = make_parts(Nt);
   long long t0 = clock64();
   for (int r = 0; r < reps; ++r) {
-    if (lane < nlanes) interior_solve(L6, dinv, vec, tmp, lane * per, lane * per + per, NT);
+    if (nlanes == 8) { if (lane < pt.P) interior_solve(L6, dinv, vec, tmp, pt.start(lane), pt.start(lane) + pt.len(lane), NT); }
+    else if (lane < nlanes) interior_solve(L6, dinv, vec, tmp, lane * per, lane * per + per, NT);
     __syncwarp();
   }
   long long t1 = clock64();
@@ -22,13 +24,15 @@ __global__ void k(long long *cyc, double *sink, int Nt, int NT, int reps, int nl
 }
 int main() {
   long long *c; double *s; cudaMalloc(&c, 64); cudaMalloc(&s, 32 * 8);
-  const int Nt = 88, NT = 96, reps = 200;
+  const int NT = 96, reps = 200;
+  for (int Nt : {88, 75, 91, 64}) {
   const int smem = (36 + 6 + 6 + 6) * NT * 8;
   for (int nl : {1, 8}) {
     k<<<1, 32, smem>>>(c, s, Nt, NT, reps, nl); cudaDeviceSynchronize();
     long long h; cudaMemcpy(&h, c, 8, cudaMemcpyDeviceToHost);
     const int per = Nt / nl;
-    printf("lanes %d: %.1f cycles per block step (fwd+bwd counted as 2 steps per block)\n", nl, (double)h / reps / (2.0 * per));
+    printf("Nt %d lanes %d: %.1f cycles per block step (fwd+bwd counted as 2 steps per block)\n", Nt, nl, (double)h / reps / (2.0 * (nl == 8 ? (Nt - 7 + 7) / 8 : per)));
+  }
   }
   printf("%s\n", cudaGetErrorString(cudaGetLastError()));
   return 0;
