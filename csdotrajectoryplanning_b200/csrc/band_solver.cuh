@@ -282,12 +282,15 @@ __device__ __noinline__ void band_factor_warp(const BandMem bm, int Nt) {
     __syncwarp();
     pt.tab = tab;
   }
+  long long dbg_t0 = clock64();
   if (lane < pt.P)
     interior_factor(bm.L6 + (pt.P == 1 ? 0 : pt.skew(lane)), bm.dinv, pt.start(lane), pt.start(lane) + pt.len(lane));
   __syncwarp();
+  DBG_T(4);
   if (pt.P == 1) return;
   if (lane < pt.P) schur_partition(bm, pt, lane);
   __syncwarp();
+  DBG_T(5);
   // F3: assemble S (dense, symmetric) and invert it in place (Gauss-Jordan, SPD: no pivoting)
   const int Ns = 6 * (pt.P - 1);
   double *S = bm.Sinv;
@@ -310,6 +313,9 @@ __device__ __noinline__ void band_factor_warp(const BandMem bm, int Nt) {
     }
   }
   __syncwarp();
+  // In-place Gauss-Jordan inversion (SPD: no pivoting).  Lane r updates rows r and r+32 with 16-byte
+  // shared-memory accesses, 6 columns per trip so the loads of a trip are in flight together; the pivot
+  // column is patched after the sweep instead of being tested inside it.  Ns is a multiple of 6.
   double *prow = bm.sv + 2 * kMaxNs;
   for (int piv = 0; piv < Ns; ++piv) {
     const double d = 1.0 / S[piv * Ns + piv];
@@ -318,13 +324,24 @@ __device__ __noinline__ void band_factor_warp(const BandMem bm, int Nt) {
     __syncwarp();
     for (int r = lane; r < Ns; r += 32) {
       if (r == piv) continue;
+      double2 *Sr = reinterpret_cast<double2 *>(S + r * Ns);
+      const double2 *pr = reinterpret_cast<const double2 *>(prow);
       const double f = S[r * Ns + piv];
-      for (int cidx = 0; cidx < Ns; ++cidx)
-        S[r * Ns + cidx] = (cidx == piv) ? -f * d : fma(-f, prow[cidx], S[r * Ns + cidx]);
+      for (int c2 = 0; c2 < Ns / 2; c2 += 3) {
+        double2 s0 = Sr[c2], s1 = Sr[c2 + 1], s2 = Sr[c2 + 2];
+        const double2 p0 = pr[c2], p1 = pr[c2 + 1], p2 = pr[c2 + 2];
+        s0.x = fma(-f, p0.x, s0.x); s0.y = fma(-f, p0.y, s0.y);
+        s1.x = fma(-f, p1.x, s1.x); s1.y = fma(-f, p1.y, s1.y);
+        s2.x = fma(-f, p2.x, s2.x); s2.y = fma(-f, p2.y, s2.y);
+        Sr[c2] = s0; Sr[c2 + 1] = s1; Sr[c2 + 2] = s2;
+      }
+      S[r * Ns + piv] = -f * d;
     }
+    __syncwarp();
     for (int cidx = lane; cidx < Ns; cidx += 32) S[piv * Ns + cidx] = prow[cidx];
     __syncwarp();
   }
+  DBG_T(6);
 }
 
 // ---- solve H x = b: b in `rhs` (SoA, overwritten by x), `tmp` is a scratch vector; one warp ----

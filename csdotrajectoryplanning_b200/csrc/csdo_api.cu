@@ -317,6 +317,7 @@ int csdo_refine(csdo_handle *h, const csdo_batch *in, csdo_result *out) {
     unsigned long long dbg[16];
     csdo::read_debug_counters(dbg);
     fprintf(stderr, "[csdo profile] solve parts: S1 %.3e  S2 %.3e  Sinv %.3e  S3 %.3e\n", (double)dbg[0], (double)dbg[1], (double)dbg[2], (double)dbg[3]);
+    fprintf(stderr, "[csdo profile] factor parts: F1 %.3e  F2 %.3e  F3 %.3e\n", (double)dbg[4], (double)dbg[5], (double)dbg[6]);
   }
   return CSDO_OK;
 }

@@ -30,9 +30,10 @@ __device__ BandFactorFn g_band_factor[2] = {band_factor_warp<false>, band_factor
 struct Box { double x_min, y_min, x_max, y_max; };
 
 struct ObsView {
-  const double *obs;  // [No][3]
+  const double *obs;  // [No][3] (staged in shared memory by the refine kernel when it fits)
   int No;
   double rv;
+  short *cand;        // kMaxCand candidate indices for the calling thread
 };
 
 // isBoxValid :252-272 restricted to the candidate list (cand == nullptr: all)
@@ -57,7 +58,7 @@ constexpr int kMaxCand = 40;
 // sequence of accepted expansions is unchanged).
 __device__ bool local_box(double xc, double yc, const ObsView &ov, double dimx, double dimy,
                           const csdo_params &P, Box &res) {
-  short cand[kMaxCand];
+  short *cand = ov.cand;  // per-thread slice (shared memory inside the refine kernel)
   int ncand = 0;
   bool overflow = false;
   const double reach = P.box_limit + 2.0 * P.box_ds + 1e-6;
@@ -74,6 +75,45 @@ __device__ bool local_box(double xc, double yc, const ObsView &ov, double dimx, 
   Box box = {xc, yc, xc, yc};
   int num_expand = 0, n_valid = 4;
   while (n_valid > 0) {
+    // Rounds that cannot fail are taken without checks: `gap` is the smallest growth of any live side
+    // that could reach a map bound or pull an obstacle centre into the inflated box, so fewer than
+    // gap/ds rounds leave every trial valid.  The box sides are still advanced by the same repeated
+    // += / -= ds, so the result is bit-identical to the reference's checked expansion.
+    {
+      double gap = 1e300;
+      if (id[0] != -1) gap = fmin(gap, (dimy - ov.rv) - box.y_max);
+      if (id[1] != -1) gap = fmin(gap, box.x_min - ov.rv);
+      if (id[2] != -1) gap = fmin(gap, box.y_min - ov.rv);
+      if (id[3] != -1) gap = fmin(gap, (dimx - ov.rv) - box.x_max);
+      const int nc = cl ? ncand : ov.No;
+      for (int q = 0; q < nc; ++q) {
+        const int o = cl ? cl[q] : q;
+        const double ox = ov.obs[3 * o], oy = ov.obs[3 * o + 1], R = ov.obs[3 * o + 2] + ov.rv;
+        // growth needed before the centre lies strictly inside the inflated box, per axis; a side that
+        // has retired cannot bring the box any closer to an obstacle lying beyond it
+        double nx = 0.0, ny = 0.0;
+        if (ox >= box.x_max + R) nx = (id[3] != -1) ? ox - (box.x_max + R) : 1e300;
+        else if (ox <= box.x_min - R) nx = (id[1] != -1) ? (box.x_min - R) - ox : 1e300;
+        if (oy >= box.y_max + R) ny = (id[0] != -1) ? oy - (box.y_max + R) : 1e300;
+        else if (oy <= box.y_min - R) ny = (id[2] != -1) ? (box.y_min - R) - oy : 1e300;
+        gap = fmin(gap, fmax(nx, ny));
+      }
+      int safe = (int)floor((gap - 1e-9) / P.box_ds) - 1;
+      for (; safe > 0 && n_valid > 0; --safe) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (id[k] == -1) continue;
+          if (k == 0) box.y_max += P.box_ds;
+          else if (k == 1) box.x_min -= P.box_ds;
+          else if (k == 2) box.y_min -= P.box_ds;
+          else box.x_max += P.box_ds;
+          num_expand++;
+          lens[k] += P.box_ds;
+          if (lens[k] >= P.box_limit) { n_valid--; id[k] = -1; }
+        }
+      }
+      if (n_valid <= 0) break;
+    }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if (id[k] == -1) continue;
@@ -144,11 +184,25 @@ __device__ void generate_box(double x, double y, const ObsView &ov, double dimx,
 // calcCorridors (float centres) / updateCorridor (double centres) for the
 // agent of this CTA: 2 boxes per step, strided over the CTA's threads.
 __device__ int agent_corridors(const Ctx &c, const csdo_params &P, const double *xs, const double *ys,
-                               const double *yaws, int stride_is_nt, bool double_centres, int *box_status) {
-  (void)stride_is_nt;
-  ObsView ov{c.obs(), c.No(), P.rv};
+                               const double *yaws, double *stage, int stage_doubles, bool double_centres,
+                               int *box_status) {
+  // Stage the instance's obstacles and the per-thread candidate lists in shared memory that is idle
+  // while corridors are generated (`stage`): global/local memory would cost an L2 round trip per access.
+  short cand_local[kMaxCand];
+  ObsView ov{c.obs(), c.No(), P.rv, cand_local};
+  const int cand_doubles = (c.nthr() * kMaxCand * (int)sizeof(short) + 7) / 8;
+  if (stage && cand_doubles <= stage_doubles) {
+    ov.cand = reinterpret_cast<short *>(stage) + c.tid() * kMaxCand;
+    double *so = stage + cand_doubles;
+    if (3 * c.No() <= stage_doubles - cand_doubles) {
+      for (int i = c.tid(); i < 3 * c.No(); i += c.nthr()) so[i] = c.obs()[i];
+      ov.obs = so;
+    }
+    __syncthreads();
+  }
   int illegal = 0;
-  for (int b = c.tid(); b < 2 * c.Nt(); b += c.nthr()) {
+  const int Nt = c.Nt();
+  for (int b = c.tid(); b < 2 * Nt; b += c.nthr()) {
     const int t = b >> 1, rear = b & 1;
     const double off = rear ? P.r2x : P.f2x;
     // separate multiply and add (the reference build has no FMA contraction)
@@ -162,10 +216,10 @@ __device__ int agent_corridors(const Ctx &c, const csdo_params &P, const double 
     generate_box(cx, cy, ov, c.dimx(), c.dimy(), P, bx, ok, init);
     if (init > 0) illegal = 1;
     const int base = rear ? 4 : 0;
-    c.corr()[(base + 0) * c.Nt() + t] = bx.x_min;
-    c.corr()[(base + 1) * c.Nt() + t] = bx.x_max;
-    c.corr()[(base + 2) * c.Nt() + t] = bx.y_min;
-    c.corr()[(base + 3) * c.Nt() + t] = bx.y_max;
+    c.corr()[(base + 0) * Nt + t] = bx.x_min;
+    c.corr()[(base + 1) * Nt + t] = bx.x_max;
+    c.corr()[(base + 2) * Nt + t] = bx.y_min;
+    c.corr()[(base + 3) * Nt + t] = bx.y_max;
     if (box_status) { box_status[2 * b] = ok; box_status[2 * b + 1] = init; }
   }
   return illegal;
@@ -936,7 +990,9 @@ __device__ __forceinline__ void refine_body(const DevBatch &B, const DevOut &O, 
     __syncthreads();
     // calcCorridors (dsqp_solver.cc:1154) on float disc centres
     PH_T0();
-    if (agent_corridors(c, P, c.guess(), c.guess() + Nt, c.guess() + 2 * Nt, 1, false, nullptr)) s_flag = 1;
+    if (agent_corridors(c, P, c.guess(), c.guess() + Nt, c.guess() + 2 * Nt, smem + LY.o_x, LY.o_carry - LY.o_x,
+                        false, nullptr))
+      s_flag = 1;
     __syncthreads();
     if (threadIdx.x == 0 && s_flag) atomicAnd(&O.inst_static_legal[inst], 0);
     __syncthreads();
@@ -969,7 +1025,8 @@ __device__ __forceinline__ void refine_body(const DevBatch &B, const DevOut &O, 
       __syncthreads();
       if (!P.fixed_corridor) {
         PH_ADD(7);
-        agent_corridors(c, P, c.sol(), c.sol() + NT, c.sol() + 2 * NT, 0, true, nullptr);
+        agent_corridors(c, P, c.sol(), c.sol() + NT, c.sol() + 2 * NT, smem + LY.o_x, LY.o_carry - LY.o_x, true,
+                        nullptr);
         __syncthreads();
         PH_ADD(0);
       }
@@ -1058,7 +1115,7 @@ __global__ void corridors_kernel(const DevBatch B, const csdo_params P, int doub
   const double *g = B.guess + 6 * off;
   if (threadIdx.x == 0) s_flag = 0;
   __syncthreads();
-  if (agent_corridors(c, P, g, g + Nt, g + 2 * Nt, 1, double_centres != 0,
+  if (agent_corridors(c, P, g, g + Nt, g + 2 * Nt, nullptr, 0, double_centres != 0,
                       box_status ? box_status + 4 * off : nullptr))
     s_flag = 1;
   __syncthreads();
