@@ -73,16 +73,21 @@ struct Ctx {
   double rho, c;    // current rho and Ruiz cost scaling (every thread holds the same value)
   long long ph[8];  // phase cycle counters (developer profiling)
 #define CSDO_GET(type, name) __device__ __forceinline__ type name() const { return s->name; }
+  // pointers into shared memory: tell the compiler, so that every use becomes LDS/STS instead of a
+  // generic load (the pointer value itself is re-read from the shared context at each use)
+#define CSDO_GET_SH(type, name) \
+  __device__ __forceinline__ type name() const { type p_ = s->name; __builtin_assume(__isShared(p_)); return p_; }
   CSDO_GET(int, Nt) CSDO_GET(int, NT) CSDO_GET(int, K) CSDO_GET(int, KP) CSDO_GET(int, No) CSDO_GET(int, KS)
   CSDO_GET(int, solver_warp) CSDO_GET(bool, l_shared)
-  CSDO_GET(double *, x) CSDO_GET(double *, xt) CSDO_GET(double *, rhs) CSDO_GET(double *, D)
-  CSDO_GET(double *, carry) CSDO_GET(double *, red) CSDO_GET(int *, pstart) CSDO_GET(double *, ros)
-  CSDO_GET(double *, cfgs) CSDO_GET(double *, Es) CSDO_GET(double *, ws)
+  CSDO_GET_SH(double *, x) CSDO_GET_SH(double *, xt) CSDO_GET_SH(double *, rhs) CSDO_GET_SH(double *, D)
+  CSDO_GET_SH(double *, carry) CSDO_GET_SH(double *, red) CSDO_GET_SH(int *, pstart) CSDO_GET_SH(double *, ros)
+  CSDO_GET_SH(double *, cfgs) CSDO_GET_SH(double *, Es) CSDO_GET_SH(double *, ws)
   CSDO_GET(double *, cur) CSDO_GET(double *, sol) CSDO_GET(double *, dy) CSDO_GET(double *, pl)
-  CSDO_GET(double *, pl_smem) CSDO_GET(double *, pl_glob)
+  CSDO_GET_SH(double *, pl_smem) CSDO_GET(double *, pl_glob)
   CSDO_GET(const double *, guess) CSDO_GET(const double *, plane_abc) CSDO_GET(const int *, plane_t)
   CSDO_GET(const double *, obs) CSDO_GET(double *, corr) CSDO_GET(double, dimx) CSDO_GET(double, dimy)
 #undef CSDO_GET
+#undef CSDO_GET_SH
   __device__ __forceinline__ const BandMem &bm() const { return s->bm; }
   // one thread per time step
   __device__ __forceinline__ int tid() const { return threadIdx.x; }
