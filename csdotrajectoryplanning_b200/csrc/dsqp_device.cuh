@@ -65,6 +65,7 @@ struct CtxShared {
   const double *obs;        // [No][3]
   double *corr;             // 8 planes, stride Nt (output array doubles as the live corridor)
   double dimx, dimy;
+  void *fn_solve, *fn_factor;  // band solve / factor entry points (indirect calls, see dsqp_kernel.cu)
 };
 
 // Per-thread handle: the shared context plus the few values that change inside a QP.
@@ -79,11 +80,11 @@ struct Ctx {
   __device__ __forceinline__ type name() const { type p_ = s->name; __builtin_assume(__isShared(p_)); return p_; }
   CSDO_GET(int, Nt) CSDO_GET(int, NT) CSDO_GET(int, K) CSDO_GET(int, KP) CSDO_GET(int, No) CSDO_GET(int, KS)
   CSDO_GET(int, solver_warp) CSDO_GET(bool, l_shared)
-  CSDO_GET_SH(double *, x) CSDO_GET_SH(double *, xt) CSDO_GET_SH(double *, rhs) CSDO_GET_SH(double *, D)
-  CSDO_GET_SH(double *, carry) CSDO_GET_SH(double *, red) CSDO_GET_SH(int *, pstart) CSDO_GET_SH(double *, ros)
-  CSDO_GET_SH(double *, cfgs) CSDO_GET_SH(double *, Es) CSDO_GET_SH(double *, ws)
+  CSDO_GET(double *, x) CSDO_GET(double *, xt) CSDO_GET(double *, rhs) CSDO_GET(double *, D)
+  CSDO_GET(double *, carry) CSDO_GET(double *, red) CSDO_GET(int *, pstart) CSDO_GET(double *, ros)
+  CSDO_GET(double *, cfgs) CSDO_GET(double *, Es) CSDO_GET(double *, ws)
   CSDO_GET(double *, cur) CSDO_GET(double *, sol) CSDO_GET(double *, dy) CSDO_GET(double *, pl)
-  CSDO_GET_SH(double *, pl_smem) CSDO_GET(double *, pl_glob)
+  CSDO_GET(double *, pl_smem) CSDO_GET(double *, pl_glob)
   CSDO_GET(const double *, guess) CSDO_GET(const double *, plane_abc) CSDO_GET(const int *, plane_t)
   CSDO_GET(const double *, obs) CSDO_GET(double *, corr) CSDO_GET(double, dimx) CSDO_GET(double, dimy)
 #undef CSDO_GET

@@ -580,7 +580,7 @@ __device__ __forceinline__ void form_and_factor(Ctx &c, const csdo_params &P) {
   __syncthreads();
   __syncwarp();
   if ((c.tid() >> 5) == c.solver_warp()) {
-    BandFactorFn fn = *(volatile BandFactorFn *)&g_band_factor[c.l_shared() ? 1 : 0];
+    BandFactorFn fn = reinterpret_cast<BandFactorFn>(c.s->fn_factor);
     fn(c.bm(), Nt);
   }
   __syncthreads();
@@ -749,7 +749,7 @@ __device__ __forceinline__ QpOut solve_qp(Ctx &c, const csdo_params &P) {
   for (iter = 1; iter <= P.osqp_max_iter; ++iter) {
     __syncwarp();  // the solver warp must enter the solve converged (threads leave barriers individually)
     if ((c.tid() >> 5) == c.solver_warp()) {
-      BandSolveFn fn = *(volatile BandSolveFn *)&g_band_solve[c.l_shared() ? 1 : 0];
+      BandSolveFn fn = reinterpret_cast<BandSolveFn>(c.s->fn_solve);  // read once per CTA from global, kept in shared
       fn(c.bm(), c.rhs(), c.xt(), Nt, NT);
 #ifdef CSDO_DOUBLE_SOLVE  // timing experiment: a second, discarded solve right after the first (warm instruction cache)
       PH_ADD(4);
@@ -920,6 +920,8 @@ __device__ __forceinline__ void refine_body(const DevBatch &B, const DevOut &O, 
     cs.bm.G = cs.xt;  // xt and rhs are contiguous and free while a factorization runs
     cs.cur = slot + LY.g_cur; cs.sol = slot + LY.g_sol; cs.dy = slot + LY.g_dy;
     cs.pl_glob = slot + LY.g_pl; cs.pl_smem = smem + LY.o_pl; cs.KS = LY.KS;
+    cs.fn_solve = reinterpret_cast<void *>(*(volatile BandSolveFn *)&g_band_solve[cs.l_shared ? 1 : 0]);
+    cs.fn_factor = reinterpret_cast<void *>(*(volatile BandFactorFn *)&g_band_factor[cs.l_shared ? 1 : 0]);
   }
 
   for (int k = 0; k < 8; ++k) c.ph[k] = 0;
