@@ -74,10 +74,6 @@ struct Ctx {
   double rho, c;    // current rho and Ruiz cost scaling (every thread holds the same value)
   long long ph[8];  // phase cycle counters (developer profiling)
 #define CSDO_GET(type, name) __device__ __forceinline__ type name() const { return s->name; }
-  // pointers into shared memory: tell the compiler, so that every use becomes LDS/STS instead of a
-  // generic load (the pointer value itself is re-read from the shared context at each use)
-#define CSDO_GET_SH(type, name) \
-  __device__ __forceinline__ type name() const { type p_ = s->name; __builtin_assume(__isShared(p_)); return p_; }
   CSDO_GET(int, Nt) CSDO_GET(int, NT) CSDO_GET(int, K) CSDO_GET(int, KP) CSDO_GET(int, No) CSDO_GET(int, KS)
   CSDO_GET(int, solver_warp) CSDO_GET(bool, l_shared)
   CSDO_GET(double *, x) CSDO_GET(double *, xt) CSDO_GET(double *, rhs) CSDO_GET(double *, D)
@@ -88,7 +84,6 @@ struct Ctx {
   CSDO_GET(const double *, guess) CSDO_GET(const double *, plane_abc) CSDO_GET(const int *, plane_t)
   CSDO_GET(const double *, obs) CSDO_GET(double *, corr) CSDO_GET(double, dimx) CSDO_GET(double, dimy)
 #undef CSDO_GET
-#undef CSDO_GET_SH
   __device__ __forceinline__ const BandMem &bm() const { return s->bm; }
   // one thread per time step
   __device__ __forceinline__ int tid() const { return threadIdx.x; }
@@ -135,6 +130,10 @@ __device__ __forceinline__ void block_reduce(double (&v)[N], double *red) {
 // ---- the rows of time step t (reference sqp/dsqp_solver.cc:646-1129) ----
 // f.row<NC>(rid, i0,c0,i1,c1,i2,c2,i3,c3, l, u, w, E): row id (0..15 fixed rows, -1 plane rows),
 // NC coefficients on local unknowns i*, raw bounds l,u, the row's ADMM state w and Ruiz factor E.
+// A functor declares which of w / E it modifies (kWriteW / kWriteE).  The per-step row data, E and w
+// of the 13 every-step rows are read into registers up front and written back once at the end: with
+// the values behind shared-memory references the compiler had to keep every load behind the previous
+// row's store (possible aliasing) and the pass ran one row at a time.
 template <class F>
 __device__ __forceinline__ void visit_rows(Ctx &c, const csdo_params &P, F &f) {
   const int t = c.t();
@@ -143,56 +142,66 @@ __device__ __forceinline__ void visit_rows(Ctx &c, const csdo_params &P, F &f) {
   __builtin_assume(__isShared(c.Es()));
   __builtin_assume(__isShared(c.ws()));
   __builtin_assume(__isShared(c.pstart()));
-  const double *ro_ = c.ros() + t;
   const int NTs = c.NT();
-#define RO(i) ro_[(i) * NTs]
+  double ro[RO_COUNT], E[13], w[13];
+  {
+    const double *ro_ = c.ros() + t, *Ep = c.Es() + t, *wp = c.ws() + t;
+#pragma unroll
+    for (int i = 0; i < RO_COUNT; ++i) ro[i] = ro_[i * NTs];
+#pragma unroll
+    for (int i = 0; i < 13; ++i) { E[i] = Ep[i * NTs]; w[i] = wp[i * NTs]; }
+  }
+  const int k0 = c.pstart()[t], k1 = c.pstart()[t + 1];
+#define RO(i) ro[i]
   const double sn = RO(RO_SN), cs = RO(RO_CS);
   if (c.has_next()) {
     // calcKineConstraint :646-744, lb = ub = -C
-    f.template row<4>(0, VX, 1.0, VP, RO(RO_A1), VV, P.dt * cs, NX, -1.0, RO(RO_KR0), RO(RO_KR0), c.ws()[0 * c.NT() + t], c.Es()[0 * c.NT() + t]);
-    f.template row<4>(1, VY, 1.0, VP, RO(RO_A2), VV, P.dt * sn, NY, -1.0, RO(RO_KR1), RO(RO_KR1), c.ws()[1 * c.NT() + t], c.Es()[1 * c.NT() + t]);
-    f.template row<4>(2, VP, 1.0, VS, RO(RO_A3), VV, RO(RO_B3), NP, -1.0, RO(RO_KR2), RO(RO_KR2), c.ws()[2 * c.NT() + t], c.Es()[2 * c.NT() + t]);
-    f.template row<3>(3, VS, 1.0, VW, P.dt * 1.0, NS, -1.0, 0, 0.0, -0.0, -0.0, c.ws()[3 * c.NT() + t], c.Es()[3 * c.NT() + t]);
+    f.template row<4>(0, VX, 1.0, VP, RO(RO_A1), VV, P.dt * cs, NX, -1.0, RO(RO_KR0), RO(RO_KR0), w[0], E[0]);
+    f.template row<4>(1, VY, 1.0, VP, RO(RO_A2), VV, P.dt * sn, NY, -1.0, RO(RO_KR1), RO(RO_KR1), w[1], E[1]);
+    f.template row<4>(2, VP, 1.0, VS, RO(RO_A3), VV, RO(RO_B3), NP, -1.0, RO(RO_KR2), RO(RO_KR2), w[2], E[2]);
+    f.template row<3>(3, VS, 1.0, VW, P.dt * 1.0, NS, -1.0, 0, 0.0, -0.0, -0.0, w[3], E[3]);
   }
   // calcCfgConstraint :746-788 (cfg = x0,xN,y0,yN,yaw0,yawN); rows 13..15 of the first/last step
-  if (t == 0) {
-    f.template row<1>(13, VX, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, c.cfgs()[0], c.cfgs()[0], c.ws()[13 * c.NT() + t], c.Es()[13 * c.NT() + t]);
-    f.template row<1>(14, VY, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, c.cfgs()[2], c.cfgs()[2], c.ws()[14 * c.NT() + t], c.Es()[14 * c.NT() + t]);
-    f.template row<1>(15, VP, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, c.cfgs()[4], c.cfgs()[4], c.ws()[15 * c.NT() + t], c.Es()[15 * c.NT() + t]);
-  }
-  if (t == c.Nt() - 1) {
-    f.template row<1>(13, VX, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, c.cfgs()[1], c.cfgs()[1], c.ws()[13 * c.NT() + t], c.Es()[13 * c.NT() + t]);
-    f.template row<1>(14, VY, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, c.cfgs()[3], c.cfgs()[3], c.ws()[14 * c.NT() + t], c.Es()[14 * c.NT() + t]);
-    f.template row<1>(15, VP, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, c.cfgs()[5], c.cfgs()[5], c.ws()[15 * c.NT() + t], c.Es()[15 * c.NT() + t]);
+  if (t == 0 || t == c.Nt() - 1) {
+    const int e = (t == 0) ? 0 : 1;
+    double *wc = c.ws() + 13 * NTs + t, *Ec = c.Es() + 13 * NTs + t;
+    f.template row<1>(13, VX, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, c.cfgs()[0 + e], c.cfgs()[0 + e], wc[0], Ec[0]);
+    f.template row<1>(14, VY, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, c.cfgs()[2 + e], c.cfgs()[2 + e], wc[NTs], Ec[NTs]);
+    f.template row<1>(15, VP, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, c.cfgs()[4 + e], c.cfgs()[4 + e], wc[2 * NTs], Ec[2 * NTs]);
   }
   // calcCorridorConstraint :874-968: D = [I,0,-f2x sin; 0,I,f2x cos; I,0,-r2x sin; 0,I,r2x cos]
-  f.template row<2>(4, VX, 1.0, VP, -P.f2x * sn, 0, 0.0, 0, 0.0, RO(RO_CL0), RO(RO_CU0), c.ws()[4 * c.NT() + t], c.Es()[4 * c.NT() + t]);
-  f.template row<2>(5, VY, 1.0, VP, P.f2x * cs, 0, 0.0, 0, 0.0, RO(RO_CL1), RO(RO_CU1), c.ws()[5 * c.NT() + t], c.Es()[5 * c.NT() + t]);
-  f.template row<2>(6, VX, 1.0, VP, -P.r2x * sn, 0, 0.0, 0, 0.0, RO(RO_CL2), RO(RO_CU2), c.ws()[6 * c.NT() + t], c.Es()[6 * c.NT() + t]);
-  f.template row<2>(7, VY, 1.0, VP, P.r2x * cs, 0, 0.0, 0, 0.0, RO(RO_CL3), RO(RO_CU3), c.ws()[7 * c.NT() + t], c.Es()[7 * c.NT() + t]);
+  f.template row<2>(4, VX, 1.0, VP, -P.f2x * sn, 0, 0.0, 0, 0.0, RO(RO_CL0), RO(RO_CU0), w[4], E[4]);
+  f.template row<2>(5, VY, 1.0, VP, P.f2x * cs, 0, 0.0, 0, 0.0, RO(RO_CL1), RO(RO_CU1), w[5], E[5]);
+  f.template row<2>(6, VX, 1.0, VP, -P.r2x * sn, 0, 0.0, 0, 0.0, RO(RO_CL2), RO(RO_CU2), w[6], E[6]);
+  f.template row<2>(7, VY, 1.0, VP, P.r2x * cs, 0, 0.0, 0, 0.0, RO(RO_CL3), RO(RO_CU3), w[7], E[7]);
   // calcTrustRegionConstraint :970-994 (centre = initial guess, all SQP iterations)
-  f.template row<1>(8, VX, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, -P.r_trust + RO(RO_TRX), P.r_trust + RO(RO_TRX), c.ws()[8 * c.NT() + t], c.Es()[8 * c.NT() + t]);
-  f.template row<1>(9, VY, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, -P.r_trust + RO(RO_TRY), P.r_trust + RO(RO_TRY), c.ws()[9 * c.NT() + t], c.Es()[9 * c.NT() + t]);
+  f.template row<1>(8, VX, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, -P.r_trust + RO(RO_TRX), P.r_trust + RO(RO_TRX), w[8], E[8]);
+  f.template row<1>(9, VY, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, -P.r_trust + RO(RO_TRY), P.r_trust + RO(RO_TRY), w[9], E[9]);
   // calcMaxCtrlAndSteerConstraint :996-1039
   if (c.has_next()) {
-    f.template row<1>(10, VV, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, -P.max_v, P.max_v, c.ws()[10 * c.NT() + t], c.Es()[10 * c.NT() + t]);
-    f.template row<1>(11, VW, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, -P.max_omega, P.max_omega, c.ws()[11 * c.NT() + t], c.Es()[11 * c.NT() + t]);
+    f.template row<1>(10, VV, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, -P.max_v, P.max_v, w[10], E[10]);
+    f.template row<1>(11, VW, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, -P.max_omega, P.max_omega, w[11], E[11]);
   }
-  f.template row<1>(12, VS, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, -P.steer_max, P.steer_max, c.ws()[12 * c.NT() + t], c.Es()[12 * c.NT() + t]);
-  // calcInterVehicleConstraint :1097-1129: 4 rows per plane of this step, l = -inf
-  const int k0 = c.pstart()[t], k1 = c.pstart()[t + 1];
-  if (c.pl() == c.pl_smem()) {  // on-chip plane rows: plain shared-memory loads (LDS), not generic ones
-    __builtin_assume(__isShared(c.pl_smem()));
-    for (int r = 4 * k0; r < 4 * k1; ++r) {
-      double *q = c.pl_smem() + (size_t)PL_COUNT * r;
-      f.template row<3>(-1, VX, q[PL_A], VY, q[PL_B], VP, q[PL_G], 0, 0.0, -INFINITY, q[PL_U], q[PL_W], q[PL_E]);
+  f.template row<1>(12, VS, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, -P.steer_max, P.steer_max, w[12], E[12]);
+#undef RO
+  {
+    double *Ep = c.Es() + t, *wp = c.ws() + t;
+#pragma unroll
+    for (int i = 0; i < 13; ++i) {
+      if (F::kWriteW) wp[i * NTs] = w[i];
+      if (F::kWriteE) Ep[i * NTs] = E[i];
     }
-  } else {
-    // overflow plane rows live in global scratch (L2 latency): one plane = 4 rows = 12 16-byte loads
-    // issued together, processed from registers, w and E written back together
-    for (int k = k0; k < k1; ++k) {
-      double2 *q2 = reinterpret_cast<double2 *>(c.pl_glob() + (size_t)PL_COUNT * 4 * k);
-      double v[4][PL_COUNT];
+  }
+  // calcInterVehicleConstraint :1097-1129: 4 rows per plane of this step, l = -inf.  One plane = 4 rows
+  // = 12 16-byte loads issued together, processed from registers, w and E written back together.
+  // On-chip plane rows use plain shared-memory loads (LDS); overflow rows live in global scratch (L2).
+  const bool on_chip = c.pl() == c.pl_smem();
+  for (int k = k0; k < k1; ++k) {
+    double v[4][PL_COUNT];
+    double2 *q2;
+    if (on_chip) {
+      __builtin_assume(__isShared(c.pl_smem()));
+      q2 = reinterpret_cast<double2 *>(c.pl_smem() + (size_t)PL_COUNT * 4 * k);
 #pragma unroll
       for (int r = 0; r < 4; ++r)
 #pragma unroll
@@ -201,16 +210,33 @@ __device__ __forceinline__ void visit_rows(Ctx &c, const csdo_params &P, F &f) {
           v[r][2 * h] = d2.x;
           v[r][2 * h + 1] = d2.y;
         }
+    } else {
+      q2 = reinterpret_cast<double2 *>(c.pl_glob() + (size_t)PL_COUNT * 4 * k);
 #pragma unroll
       for (int r = 0; r < 4; ++r)
-        f.template row<3>(-1, VX, v[r][PL_A], VY, v[r][PL_B], VP, v[r][PL_G], 0, 0.0, -INFINITY, v[r][PL_U],
-                          v[r][PL_W], v[r][PL_E]);
 #pragma unroll
-      for (int r = 0; r < 4; ++r)
-        q2[r * (PL_COUNT / 2) + PL_E / 2] = make_double2(v[r][PL_E], v[r][PL_W]);
+        for (int h = 0; h < PL_COUNT / 2; ++h) {
+          const double2 d2 = q2[r * (PL_COUNT / 2) + h];
+          v[r][2 * h] = d2.x;
+          v[r][2 * h + 1] = d2.y;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      f.template row<3>(-1, VX, v[r][PL_A], VY, v[r][PL_B], VP, v[r][PL_G], 0, 0.0, -INFINITY, v[r][PL_U],
+                        v[r][PL_W], v[r][PL_E]);
+    if (F::kWriteW || F::kWriteE) {
+      if (on_chip) {
+        __builtin_assume(__isShared(c.pl_smem()));
+        double2 *s2 = reinterpret_cast<double2 *>(c.pl_smem() + (size_t)PL_COUNT * 4 * k);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) s2[r * (PL_COUNT / 2) + PL_E / 2] = make_double2(v[r][PL_E], v[r][PL_W]);
+      } else {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) q2[r * (PL_COUNT / 2) + PL_E / 2] = make_double2(v[r][PL_E], v[r][PL_W]);
+      }
     }
   }
-#undef RO
 }
 
 // rho of a row from its scaled bounds (OSQP set_rho_vec; "loose" rows cannot occur)

@@ -254,6 +254,7 @@ __device__ __forceinline__ void row_scatter(double (&acc)[10], double g, int i0,
 //   MODE 3: re-base after a rho update (keeps z and y, osqp_update_rho)
 template <int MODE>
 struct StepF {
+  static constexpr bool kWriteW = true, kWriteE = false;
   double xv[10];
   double acc[10];
   double alpha, rho, rho_old;
@@ -299,6 +300,7 @@ enum Norm : int {
   N_DY, N_ATDY, N_COUNT
 };
 struct CheckF {
+  static constexpr bool kWriteW = false, kWriteE = false;
   double xv[10];
   double acc[10];   // A'y (raw-space accumulation)
   double accd[10];  // A'delta_y
@@ -336,6 +338,7 @@ struct CheckF {
 
 // one Ruiz pass over the rows (OSQP scale_data): row norms -> E, column maxima
 struct ScaleF {
+  static constexpr bool kWriteW = false, kWriteE = true;
   double dv[10];    // current D of the touched unknowns
   double cmax[10];  // max_i E_i |a_ij| per touched unknown (without D_j)
   template <int NC>
@@ -354,6 +357,7 @@ struct ScaleF {
 
 // reset E to 1 before scaling
 struct ResetF {
+  static constexpr bool kWriteW = true, kWriteE = true;
   template <int NC>
   __device__ __forceinline__ void row(int, int, double, int, double, int, double, int, double, double, double,
                                       double &w, double &E) {
@@ -365,6 +369,7 @@ struct ResetF {
 // A' diag(rho E^2) A in raw space: own 6x6 block (lower triangle), the coupling
 // to the next step and the next step's diagonal contributions.
 struct HasmF {
+  static constexpr bool kWriteW = false, kWriteE = false;
   double q[6][6];   // q[i][j], j <= i
   double cr[4][6];  // rows = next-step x,y,yaw,steer; cols = own unknowns
   double nd[4];
