@@ -1,23 +1,27 @@
 // Horizon-partitioned LDL' of the reduced KKT matrix (block tridiagonal, 6x6
 // blocks, scalar half-bandwidth 6) and the matching solve, run by ONE warp.
 //
-// The Nt time blocks are cut into P <= 8 partitions separated by P-1 single
+// The Nt time blocks are cut into P <= 16 partitions separated by P-1 single
 // "separator" blocks (a nested-dissection ordering of the same matrix, so the
 // solve is still an exact direct solve; only rounding differs from a
 // sequential band factor):
 //     [interior_0][sep_0][interior_1][sep_1] ... [interior_{P-1}]
-// Lane p owns partition p.
+// Lane p owns partition p.  The separator system S (block tridiagonal, P-1
+// blocks) is dissected once more: for P in {8, 12, 16} every (nb+1)-th
+// separator (nb = 1, 2, 3) is a level-2 separator, the 4 groups of nb
+// separators between them and the 3 level-2 separators' Schur complement R are
+// inverted densely (<= 18 x 18 each); for P <= 4 all separators form R.
 //   factor:  F1  banded LDL' of every interior (lanes in lockstep)
 //            F2  Schur complement of the separators, streamed per partition
-//            F3  dense inverse of the (6(P-1))^2 separator system (whole warp)
+//            F3  level 2: group inverses, R, R^-1 (whole warp, dense)
 //   solve :  S1  z_p = H_pp^-1 b_p                (forward + backward sweeps)
-//            S2  g = b_sep - coupling * z ; x_sep = Sinv g   (warp mat-vec)
+//            S2  g = b_sep - coupling * z ; x_sep = S^-1 g  (level-2 mat-vecs)
 //            S3  x_p = H_pp^-1 (b_p - coupling * x_sep)      (two more sweeps)
 // A sweep step handles one 6x6 block from registers: the part that depends on
 // the neighbouring block is 6 independent DFMA chains, the intra-block triangle
 // runs in outer-product order, so the loop-carried chain is ~6 DFMAs per block
 // and the step is bound by the issue rate of one warp (measured, see
-// scripts/micro/sweep_bench.cu).
+// scripts/micro/sweep_bench.cu) -- hence many short partitions.
 //
 // Storage (time-major row i = 6 t + k; every block has 6 rows -- the last time
 // step's missing v, w are dummy unknowns with H_ii = 1 and zero coupling):
@@ -34,8 +38,7 @@ namespace csdo {
 __device__ unsigned long long g_dbg[16];  // developer counters (CSDO_PROFILE)
 #define DBG_T(i) do { if (lane == 0) { long long t_ = clock64(); atomicAdd(&g_dbg[i], (unsigned long long)(t_ - dbg_t0)); dbg_t0 = t_; } } while (0)
 
-constexpr int kMaxP = 8;
-constexpr int kMaxNs = 6 * (kMaxP - 1);  // separator unknowns
+#define DBG_TB(i) do { if (lane == 0) { long long t_ = clock64(); atomicAdd(&g_dbg[i], (unsigned long long)(t_ - dbg_t0b)); dbg_t0b = t_; } } while (0)
 
 struct Parts {
   int P, base, rem;
@@ -44,18 +47,11 @@ struct Parts {
   __device__ __forceinline__ int sep(int j) const { return start(j) + len(j); }  // block index of separator j
   // Bank skew (in doubles) of the rows of partition p / separator p: the lanes of the solver warp read
   // their blocks with LDS.128 in lockstep; shifting partition p so that its rows start at 16-byte
-  // slot p (mod 8) of the 128-byte bank window makes those 8 loads conflict-free (a block is 288 B).
-  // The offsets accumulate (each partition is pushed 0..7 slots further than the previous one), so the
-  // shifted partitions never overlap.
-  int off[8];
-  const int *tab = nullptr;  // optional copy of off[] in shared memory (cheap runtime indexing)
-  __device__ __forceinline__ int skew(int p) const {
-    if (tab) return tab[p];
-    int r = 0;  // select chain: keeps off[] in registers
-#pragma unroll
-    for (int q = 0; q < 8; ++q) r = (q == p) ? off[q] : r;
-    return r;
-  }
+  // slot p (mod 8) of the 128-byte bank window makes 8 neighbouring loads conflict-free (a block is
+  // 288 B).  The offsets accumulate (each partition is pushed 0..7 slots further than the previous
+  // one), so the shifted partitions never overlap.  The table lives in the shared context.
+  const int *tab;
+  __device__ __forceinline__ int skew(int p) const { return tab[p]; }
   // partition that owns block t (a separator belongs to the partition above it)
   __device__ __forceinline__ int owner(int t) const {
     const int big = rem * (base + 2);
@@ -63,23 +59,44 @@ struct Parts {
   }
   __device__ __forceinline__ int skew_of_block(int t) const { return P == 1 ? 0 : skew(owner(t)); }
 };
-constexpr int kSkewPad = 128;  // extra doubles at the end of the L6 area (<= 8 partitions x 14 doubles)
 
-__device__ __forceinline__ Parts make_parts(int Nt) {
+// P in {1, 2, 3, 4, 8, 12, 16}: at least ~4 interior blocks per partition
+__device__ __forceinline__ Parts make_parts(int Nt, const int *tab) {
   Parts q;
   int P = (Nt + 1) / 8;
-  P = P < 1 ? 1 : (P > kMaxP ? kMaxP : P);
+  P = P < 1 ? 1 : P;
+  if (P > 4) P = Nt >= 80 ? 16 : (Nt >= 60 ? 12 : 8);
   q.P = P;
   const int interior = Nt - (P - 1);
   q.base = interior / P;
   q.rem = interior % P;
-  int acc16 = 0;  // accumulated shift in 16-byte slots
-#pragma unroll
-  for (int p = 0; p < 8; ++p) {
-    if (p < P && P > 1) acc16 += (p - (18 * q.start(p) + acc16)) & 7;
-    q.off[p] = 2 * acc16;
-  }
+  q.tab = tab;
   return q;
+}
+// fills the skew table (kMaxP ints) of a horizon; one thread
+__device__ __forceinline__ void fill_skew_table(int Nt, int *tab) {
+  const Parts q = make_parts(Nt, tab);
+  int acc16 = 0;  // accumulated shift in 16-byte slots
+  for (int p = 0; p < kMaxP; ++p) {
+    if (p < q.P && q.P > 1) acc16 += (p - (18 * q.start(p) + acc16)) & 7;
+    tab[p] = 2 * acc16;
+  }
+}
+
+// level-2 dissection of the P-1 separators
+struct Lvl2 {
+  int nb;   // separators per group (0: no groups, all separators are level-2 separators)
+  int ns2;  // level-2 separators
+  __device__ __forceinline__ int n_g() const { return 6 * nb; }
+  __device__ __forceinline__ int n_r() const { return 6 * ns2; }
+  __device__ __forceinline__ int sigma(int s) const { return nb ? s * (nb + 1) + nb : s; }  // separator index
+};
+__device__ __forceinline__ Lvl2 make_lvl2(int P) {
+  Lvl2 l;
+  const int Ps = P - 1;
+  if (Ps <= 3) { l.nb = 0; l.ns2 = Ps; }
+  else { l.nb = (Ps - 3) / 4; l.ns2 = 3; }
+  return l;
 }
 
 // ---- F1: interior banded LDL' of blocks [t0, t1) (columns before 6*t0 are ignored) ----
@@ -267,6 +284,38 @@ __device__ void schur_partition(const BandMem &bm, const Parts &pt, int p) {
   }
 }
 
+// In-place Gauss-Jordan inversion of an n x n SPD matrix (no pivoting) by a group of `gs` lanes
+// (lane index lg in the group); prow = n doubles of scratch.  All lanes of the warp call it together.
+__device__ __forceinline__ void gj_invert(double *M, int n, int lg, int gs, double *prow, bool active) {
+  for (int piv = 0; piv < n; ++piv) {
+    const double d = active ? 1.0 / M[piv * n + piv] : 0.0;
+    __syncwarp();
+    if (active)
+      for (int cidx = lg; cidx < n; cidx += gs) prow[cidx] = (cidx == piv) ? d : M[piv * n + cidx] * d;
+    __syncwarp();
+    if (active)
+      for (int r = lg; r < n; r += gs) {
+        if (r == piv) continue;
+        double2 *Mr = reinterpret_cast<double2 *>(M + r * n);
+        const double2 *pr = reinterpret_cast<const double2 *>(prow);
+        const double f = M[r * n + piv];
+        for (int c2 = 0; c2 < n / 2; c2 += 3) {  // n is a multiple of 6
+          double2 s0 = Mr[c2], s1 = Mr[c2 + 1], s2 = Mr[c2 + 2];
+          const double2 p0 = pr[c2], p1 = pr[c2 + 1], p2 = pr[c2 + 2];
+          s0.x = fma(-f, p0.x, s0.x); s0.y = fma(-f, p0.y, s0.y);
+          s1.x = fma(-f, p1.x, s1.x); s1.y = fma(-f, p1.y, s1.y);
+          s2.x = fma(-f, p2.x, s2.x); s2.y = fma(-f, p2.y, s2.y);
+          Mr[c2] = s0; Mr[c2 + 1] = s1; Mr[c2 + 2] = s2;
+        }
+        M[r * n + piv] = -f * d;
+      }
+    __syncwarp();
+    if (active)
+      for (int cidx = lg; cidx < n; cidx += gs) M[piv * n + cidx] = prow[cidx];
+    __syncwarp();
+  }
+}
+
 // ---- whole factorization, executed by one warp (all 32 lanes call it) ----
 // __noinline__: the factor/solve get their own register allocation instead of competing with the
 // register-resident row state of the caller (saved/restored around the call by the solver warp only)
@@ -274,14 +323,9 @@ template <bool SH>
 __device__ __noinline__ void band_factor_warp(const BandMem bm, int Nt) {
   if (SH) { __builtin_assume(__isShared(bm.L6)); __builtin_assume(__isShared(bm.dinv)); }
   __builtin_assume(__isShared(bm.Sinv)); __builtin_assume(__isShared(bm.sv)); __builtin_assume(__isShared(bm.G));
-  Parts pt = make_parts(Nt);
+  __builtin_assume(__isShared(bm.tab));
+  const Parts pt = make_parts(Nt, bm.tab);
   const int lane = threadIdx.x & 31;
-  {
-    int *tab = reinterpret_cast<int *>(bm.sv + 3 * kMaxNs);
-    if (lane < 8) tab[lane] = pt.skew(lane);
-    __syncwarp();
-    pt.tab = tab;
-  }
   long long dbg_t0 = clock64();
   if (lane < pt.P)
     interior_factor(bm.L6 + (pt.P == 1 ? 0 : pt.skew(lane)), bm.dinv, pt.start(lane), pt.start(lane) + pt.len(lane));
@@ -291,57 +335,172 @@ __device__ __noinline__ void band_factor_warp(const BandMem bm, int Nt) {
   if (lane < pt.P) schur_partition(bm, pt, lane);
   __syncwarp();
   DBG_T(5);
-  // F3: assemble S (dense, symmetric) and invert it in place (Gauss-Jordan, SPD: no pivoting)
-  const int Ns = 6 * (pt.P - 1);
-  double *S = bm.Sinv;
-  for (int e = lane; e < Ns * Ns; e += 32) S[e] = 0.0;
+  // F3: level 2.  S has diagonal blocks A_j = H_TT - GBB(partition j) - GCC(partition j+1) and
+  // sub-diagonal blocks B_j = S[j][j-1] = -GBC(partition j).
+  const Lvl2 l2 = make_lvl2(pt.P);
+  const int Ps = pt.P - 1, nb = l2.nb, n_g = l2.n_g(), nR = l2.n_r();
+  double *Tinv = bm.Sinv, *R = bm.Sinv + kL2Tinv, *Bc = R + kL2R;
+  long long dbg_t0b = clock64();
+  for (int e = lane; e < 4 * n_g * n_g; e += 32) Tinv[e] = 0.0;
+  for (int e = lane; e < nR * nR; e += 32) R[e] = 0.0;
   __syncwarp();
-  for (int e = lane; e < (pt.P - 1) * 36; e += 32) {
+  for (int e = lane; e < Ps * 36; e += 32) {
     const int j = e / 36, a = (e % 36) / 6, b = e % 6;  // separator j, entry (a, b) of its 6x6 blocks
     const int T = pt.sep(j);
-    // diagonal block: H_TT - GBB(partition j) - GCC(partition j+1)
     const int hi = a > b ? a : b, lo = a > b ? b : a;
     double v = (a == b) ? bm.dinv[6 * T + a] : bm.L6[pt.skew(j) + (size_t)(6 * T + hi) * 6 + (hi - lo) - 1];
     const int q = hi * (hi + 1) / 2 + lo;
     v -= bm.G[j * 78 + 21 + q];
     v -= bm.G[(j + 1) * 78 + q];
-    S[(6 * j + a) * Ns + 6 * j + b] = v;
-    if (j > 0) {  // coupling to the previous separator through partition j: -GBC(partition j)
-      const double c = -bm.G[j * 78 + 42 + a * 6 + b];
-      S[(6 * j + a) * Ns + 6 * (j - 1) + b] = c;
-      S[(6 * (j - 1) + b) * Ns + 6 * j + a] = c;
+    const double cpl = j > 0 ? -bm.G[j * 78 + 42 + a * 6 + b] : 0.0;  // B_j[a][b]
+    if (nb == 0) {
+      R[(6 * j + a) * nR + 6 * j + b] = v;
+      if (j > 0) { R[(6 * j + a) * nR + 6 * (j - 1) + b] = cpl; R[(6 * (j - 1) + b) * nR + 6 * j + a] = cpl; }
+    } else {
+      const int g = j / (nb + 1), i = j % (nb + 1);
+      if (i < nb) {  // member i of group g
+        double *Tg = Tinv + g * n_g * n_g;
+        Tg[(6 * i + a) * n_g + 6 * i + b] = v;
+        if (i > 0) { Tg[(6 * i + a) * n_g + 6 * (i - 1) + b] = cpl; Tg[(6 * (i - 1) + b) * n_g + 6 * i + a] = cpl; }
+        else if (g > 0) Bc[(2 * (g - 1) + 1) * 36 + a * 6 + b] = cpl;  // first member <-> level-2 separator g-1
+      } else {  // level-2 separator g
+        R[(6 * g + a) * nR + 6 * g + b] = v;
+        Bc[(2 * g) * 36 + a * 6 + b] = cpl;  // level-2 separator g <-> last member of group g
+      }
     }
   }
   __syncwarp();
-  // In-place Gauss-Jordan inversion (SPD: no pivoting).  Lane r updates rows r and r+32 with 16-byte
-  // shared-memory accesses, 6 columns per trip so the loads of a trip are in flight together; the pivot
-  // column is patched after the sweep instead of being tested inside it.  Ns is a multiple of 6.
-  double *prow = bm.sv + 2 * kMaxNs;
-  for (int piv = 0; piv < Ns; ++piv) {
-    const double d = 1.0 / S[piv * Ns + piv];
-    __syncwarp();
-    for (int cidx = lane; cidx < Ns; cidx += 32) prow[cidx] = (cidx == piv) ? d : S[piv * Ns + cidx] * d;
-    __syncwarp();
-    for (int r = lane; r < Ns; r += 32) {
-      if (r == piv) continue;
-      double2 *Sr = reinterpret_cast<double2 *>(S + r * Ns);
-      const double2 *pr = reinterpret_cast<const double2 *>(prow);
-      const double f = S[r * Ns + piv];
-      for (int c2 = 0; c2 < Ns / 2; c2 += 3) {
-        double2 s0 = Sr[c2], s1 = Sr[c2 + 1], s2 = Sr[c2 + 2];
-        const double2 p0 = pr[c2], p1 = pr[c2 + 1], p2 = pr[c2 + 2];
-        s0.x = fma(-f, p0.x, s0.x); s0.y = fma(-f, p0.y, s0.y);
-        s1.x = fma(-f, p1.x, s1.x); s1.y = fma(-f, p1.y, s1.y);
-        s2.x = fma(-f, p2.x, s2.x); s2.y = fma(-f, p2.y, s2.y);
-        Sr[c2] = s0; Sr[c2 + 1] = s1; Sr[c2 + 2] = s2;
+  DBG_TB(7);
+  if (nb) {
+    // the 4 group inverses, 8 lanes each
+    gj_invert(Tinv + (lane >> 3) * n_g * n_g, n_g, lane & 7, 8, bm.sv + 2 * kMaxNs + (lane >> 3) * 18, true);
+    DBG_TB(8);
+    // R -= couplings * Tinv * couplings
+    const int lo6 = n_g - 6;
+    for (int e = lane; e < 5 * 36; e += 32) {
+      const int blk = e / 36, a = (e % 36) / 6, b = e % 6;
+      if (blk < 3) {
+        const int s = blk;
+        const double *Bl = Bc + (2 * s) * 36, *Br = Bc + (2 * s + 1) * 36;
+        const double *Tl = Tinv + s * n_g * n_g, *Tr = Tinv + (s + 1) * n_g * n_g;
+        double acc = 0.0;
+        for (int cc = 0; cc < 6; ++cc) {
+          double t1 = 0.0, t2 = 0.0;
+          for (int d = 0; d < 6; ++d) {
+            t1 = fma(Tl[(lo6 + cc) * n_g + lo6 + d], Bl[b * 6 + d], t1);
+            t2 = fma(Tr[cc * n_g + d], Br[d * 6 + b], t2);
+          }
+          acc = fma(Bl[a * 6 + cc], t1, acc);
+          acc = fma(Br[cc * 6 + a], t2, acc);
+        }
+        R[(6 * s + a) * nR + 6 * s + b] -= acc;
+      } else {
+        const int s = blk - 3;  // R[s+1][s] through group s+1
+        const double *Bu = Bc + (2 * (s + 1)) * 36, *Bd = Bc + (2 * s + 1) * 36;
+        const double *Tm = Tinv + (s + 1) * n_g * n_g;
+        double acc = 0.0;
+        for (int cc = 0; cc < 6; ++cc) {
+          double t1 = 0.0;
+          for (int d = 0; d < 6; ++d) t1 = fma(Tm[(lo6 + cc) * n_g + d], Bd[d * 6 + b], t1);
+          acc = fma(Bu[a * 6 + cc], t1, acc);
+        }
+        R[(6 * (s + 1) + a) * nR + 6 * s + b] = -acc;
+        R[(6 * s + b) * nR + 6 * (s + 1) + a] = -acc;
       }
-      S[r * Ns + piv] = -f * d;
     }
     __syncwarp();
-    for (int cidx = lane; cidx < Ns; cidx += 32) S[piv * Ns + cidx] = prow[cidx];
-    __syncwarp();
+    DBG_TB(9);
   }
+  gj_invert(R, nR, lane, 32, bm.sv + 2 * kMaxNs, true);
+  DBG_TB(10);
   DBG_T(6);
+}
+
+// y_G = Tinv_G v_G for the 4 groups: v and y are separator vectors (group G at offset G * 6 (NB + 1))
+template <int NB>
+__device__ __forceinline__ void group_matvec(const double *Tinv, const double *v, double *y, int lane) {
+  constexpr int NG = 6 * NB, ROWS = 4 * NG, TRIPS = (ROWS + 31) / 32, GS = 6 * (NB + 1);
+#pragma unroll
+  for (int tr = 0; tr < TRIPS; ++tr) {
+    const int e = lane + 32 * tr;
+    const bool on = e < ROWS;
+    const int ee = on ? e : 0;
+    const int G = ee / NG, r = ee % NG;
+    const double2 *Tr = reinterpret_cast<const double2 *>(Tinv + G * NG * NG + r * NG);
+    const double2 *gv = reinterpret_cast<const double2 *>(v + G * GS);
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int c2 = 0; c2 < NG / 2; ++c2) {
+      const double2 tv = Tr[c2], gg = gv[c2];
+      s0 = fma(tv.x, gg.x, s0);
+      s1 = fma(tv.y, gg.y, s1);
+    }
+    if (on) y[G * GS + r] = s0 + s1;
+  }
+}
+
+// x_sep = S^-1 g for 4 groups of NB separators and 3 level-2 separators (g, x_sep, z in bm.sv)
+template <int NB>
+__device__ __forceinline__ void lvl2_solve(const BandMem &bm, int lane) {
+  constexpr int NG = 6 * NB, GS = 6 * (NB + 1);
+  const double *Tinv = bm.Sinv, *Rinv = bm.Sinv + kL2Tinv, *Bc = Rinv + kL2R;
+  double *g = bm.sv, *xs = bm.sv + kMaxNs, *z = bm.sv + 2 * kMaxNs;
+  // 1. z_G = Tinv_G g_G
+  group_matvec<NB>(Tinv, g, z, lane);
+  __syncwarp();
+  // 2. level-2 right-hand side r = g_sigma - couplings * z (kept in registers, exchanged by shuffles)
+  double r = 0.0;
+  {
+    const int l18 = lane < 18 ? lane : 0, s = l18 / 6, a = l18 % 6;
+    const double *Bl = Bc + (2 * s) * 36, *Br = Bc + (2 * s + 1) * 36;
+    const double *zl = z + s * GS + (NG - 6), *zr = z + (s + 1) * GS;
+    double r0 = g[s * GS + NG + a], r1 = 0.0;
+#pragma unroll
+    for (int cc = 0; cc < 6; ++cc) { r0 = fma(-Bl[a * 6 + cc], zl[cc], r0); r1 = fma(-Br[cc * 6 + a], zr[cc], r1); }
+    r = r0 + r1;
+  }
+  // 3. level-2 separators: x_sigma = Rinv r
+  double xsig;
+  {
+    const double *Rr = Rinv + (lane < 18 ? lane : 0) * 18;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll
+    for (int b = 0; b < 18; b += 3) {
+      s0 = fma(Rr[b], __shfl_sync(0xffffffffu, r, b), s0);
+      s1 = fma(Rr[b + 1], __shfl_sync(0xffffffffu, r, b + 1), s1);
+      s2 = fma(Rr[b + 2], __shfl_sync(0xffffffffu, r, b + 2), s2);
+    }
+    xsig = (s0 + s1) + s2;
+    if (lane < 18) xs[(lane / 6) * GS + NG + lane % 6] = xsig;
+  }
+  // 4. move the level-2 solution to the groups' right-hand sides (first / last member of a group);
+  //    every lane takes part in the shuffles
+  {
+    const int l24 = lane < 24 ? lane : 0, G = l24 / 6, a = l24 % 6;
+    const int sp = G > 0 ? G - 1 : 0, sn = G < 3 ? G : 0;
+    const double *Bd = Bc + (2 * sp + 1) * 36, *Bu = Bc + (2 * sn) * 36;
+    double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+    for (int b = 0; b < 6; ++b) {
+      const double xp = __shfl_sync(0xffffffffu, xsig, 6 * sp + b), xn = __shfl_sync(0xffffffffu, xsig, 6 * sn + b);
+      d0 = fma(Bd[a * 6 + b], xp, d0);
+      d1 = fma(Bu[b * 6 + a], xn, d1);
+    }
+    if (G == 0) d0 = 0.0;
+    if (G == 3) d1 = 0.0;
+    if (lane < 24) {
+      if (NB == 1) {
+        g[G * GS + a] -= d0 + d1;
+      } else {
+        if (G > 0) g[G * GS + a] -= d0;
+        if (G < 3) g[G * GS + (NG - 6) + a] -= d1;
+      }
+    }
+  }
+  __syncwarp();
+  // 5. x_G = Tinv_G g_G
+  group_matvec<NB>(Tinv, g, xs, lane);
+  __syncwarp();
 }
 
 // ---- solve H x = b: b in `rhs` (SoA, overwritten by x), `tmp` is a scratch vector; one warp ----
@@ -350,14 +509,9 @@ __device__ __noinline__ void band_solve_warp(const BandMem bm, double *rhs, doub
   if (SH) { __builtin_assume(__isShared(bm.L6)); __builtin_assume(__isShared(bm.dinv)); }
   __builtin_assume(__isShared(bm.Sinv)); __builtin_assume(__isShared(bm.sv));
   __builtin_assume(__isShared(rhs)); __builtin_assume(__isShared(tmp));
-  Parts pt = make_parts(Nt);
+  __builtin_assume(__isShared(bm.tab));
+  const Parts pt = make_parts(Nt, bm.tab);
   const int lane = threadIdx.x & 31;
-  {
-    int *tab = reinterpret_cast<int *>(bm.sv + 3 * kMaxNs);
-    if (lane < 8) tab[lane] = pt.skew(lane);
-    __syncwarp();
-    pt.tab = tab;
-  }
   if (pt.P == 1) {
     if (lane == 0) interior_solve(bm.L6, bm.dinv, rhs, rhs, 0, Nt, NT);
     __syncwarp();
@@ -370,7 +524,7 @@ __device__ __noinline__ void band_solve_warp(const BandMem bm, double *rhs, doub
   __syncwarp();
   DBG_T(0);
   const int Ns = 6 * (pt.P - 1);
-  double *g = bm.sv, *xs = bm.sv + kMaxNs;
+  double *g = bm.sv, *xs = bm.sv + kMaxNs, *z = bm.sv + 2 * kMaxNs;
   for (int e = lane; e < Ns; e += 32) {  // S2: separator right-hand side
     const int j = e / 6, k = e % 6, T = pt.sep(j);
     double s = rhs[k * NT + T];
@@ -384,17 +538,25 @@ __device__ __noinline__ void band_solve_warp(const BandMem bm, double *rhs, doub
   }
   __syncwarp();
   DBG_T(1);
-  for (int r = lane; r < Ns; r += 32) {  // x_sep = Sinv g
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-    const double *Sr = bm.Sinv + r * Ns;
-#pragma unroll 2
-    for (int cidx = 0; cidx < Ns; cidx += 6) {  // Ns is a multiple of 6
-      s0 = fma(Sr[cidx], g[cidx], s0); s1 = fma(Sr[cidx + 1], g[cidx + 1], s1); s2 = fma(Sr[cidx + 2], g[cidx + 2], s2);
-      s0 = fma(Sr[cidx + 3], g[cidx + 3], s0); s1 = fma(Sr[cidx + 4], g[cidx + 4], s1); s2 = fma(Sr[cidx + 5], g[cidx + 5], s2);
+  // x_sep = S^-1 g through the level-2 dissection
+  const Lvl2 l2 = make_lvl2(pt.P);
+  if (l2.nb == 0) {
+    const int nR = l2.n_r();
+    const double *Rinv = bm.Sinv + kL2Tinv;
+    if (lane < nR) {
+      double s0 = 0.0, s1 = 0.0;
+      const double *Rr = Rinv + lane * nR;
+      for (int cidx = 0; cidx < nR; cidx += 2) { s0 = fma(Rr[cidx], g[cidx], s0); s1 = fma(Rr[cidx + 1], g[cidx + 1], s1); }
+      xs[lane] = s0 + s1;
     }
-    xs[r] = (s0 + s1) + s2;
+    __syncwarp();
+  } else if (l2.nb == 1) {
+    lvl2_solve<1>(bm, lane);
+  } else if (l2.nb == 2) {
+    lvl2_solve<2>(bm, lane);
+  } else {
+    lvl2_solve<3>(bm, lane);
   }
-  __syncwarp();
   DBG_T(2);
   for (int e = lane; e < Ns; e += 32) rhs[(e % 6) * NT + pt.sep(e / 6)] = xs[e];
   if (lane < pt.P) {  // S3: interiors with the separator solution moved to the right-hand side

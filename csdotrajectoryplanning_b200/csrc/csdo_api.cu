@@ -146,17 +146,23 @@ int run_refine(csdo_handle *h, const DevBatch &B, const DevOut &O, int max_nt, i
   if (max_nt > kMaxThreads) { h->err = "horizon exceeds 512 steps"; return CSDO_ERR_UNSUPPORTED; }
   const int NT = (max_nt + 31) & ~31;
   const int KMAX = std::max(4, (max_k + 3) & ~3);
-  // placement: keep the band factor in shared memory whenever it fits (tier 0: everything
-  // shared; tier 1: read-only row data in global); tier 2 (factor in global) only for long horizons
+  // placement (tier bit 0: row data / scaling / state in global scratch, bit 1: band factor in global
+  // scratch): everything in shared memory when that already allows the most resident CTAs, else the
+  // row arrays move out (they are read once per pass into registers); the factor moves last
   const int block = std::max(64, NT);
   Layout LY{};
   int occ = 0;
-  for (int tier = 0; tier <= 2; tier += 2) {   // 0: band factor in shared memory, 2: in global scratch
-    if (tier == 2 && occ > 0) break;
+  bool lean = false;  // kernel variant compiled with fewer registers for one more resident CTA
+  const char *force = getenv("CSDO_TIER");  // developer knob
+  for (int tier = 0; tier <= 3; ++tier) {
+    if (force && tier != atoi(force)) continue;
+    if (!force && tier >= 2 && occ > 0) break;
     const Layout l = make_layout(NT, KMAX, tier, 0);
     if (l.smem_doubles * 8 + 1024 > h->smem_limit) continue;
-    const int o = refine_occupancy(block, l.smem_doubles * 8);
-    if (o > occ) { occ = o; LY = l; }
+    for (int ln = 0; ln < 2; ++ln) {
+      const int o = refine_occupancy(block, l.smem_doubles * 8, ln);
+      if (o > occ) { occ = o; LY = l; lean = ln; }
+    }
   }
   if (occ >= 1) {
     // spend the shared memory that the chosen residency leaves free on the agents' plane rows
@@ -165,7 +171,7 @@ int run_refine(csdo_handle *h, const DevBatch &B, const DevOut &O, int max_nt, i
     int KS = std::min(KMAX, std::max(0, budget / (PL_BYTES_PER_PLANE)));
     KS &= ~1;
     Layout l = make_layout(NT, KMAX, LY.tier, KS);
-    if (refine_occupancy(block, l.smem_doubles * 8) >= occ) LY = l;
+    if (refine_occupancy(block, l.smem_doubles * 8, lean) >= occ) LY = l;
   }
   if (occ < 1) { h->err = "horizon does not fit the kernel's shared-memory layout"; return CSDO_ERR_UNSUPPORTED; }
   if (const char *cap = getenv("CSDO_MAX_CTAS_PER_SM")) occ = std::max(1, std::min(occ, atoi(cap)));  // developer knob
@@ -175,7 +181,7 @@ int run_refine(csdo_handle *h, const DevBatch &B, const DevOut &O, int max_nt, i
   if ((rc = ensure(h, h->queue, 2048))) return rc;
   if (set_err(h, "launch_refine",
               launch_refine(B, O, h->P, LY, static_cast<double *>(h->scratch.p), static_cast<int *>(h->queue.p),
-                            grid, block, stream)))
+                            grid, block, lean, stream)))
     return CSDO_ERR_CUDA;
   h->last.launches = 3;
   h->last.grid = grid; h->last.block = block; h->last.smem_bytes = LY.smem_doubles * 8;
@@ -317,7 +323,8 @@ int csdo_refine(csdo_handle *h, const csdo_batch *in, csdo_result *out) {
     unsigned long long dbg[16];
     csdo::read_debug_counters(dbg);
     fprintf(stderr, "[csdo profile] solve parts: S1 %.3e  S2 %.3e  Sinv %.3e  S3 %.3e\n", (double)dbg[0], (double)dbg[1], (double)dbg[2], (double)dbg[3]);
-    fprintf(stderr, "[csdo profile] factor parts: F1 %.3e  F2 %.3e  F3 %.3e\n", (double)dbg[4], (double)dbg[5], (double)dbg[6]);
+    fprintf(stderr, "[csdo profile] factor parts: F1 %.3e  F2 %.3e  F3 %.3e (scatter %.3e  groups %.3e  R %.3e  Rinv %.3e)\n",
+            (double)dbg[4], (double)dbg[5], (double)dbg[6], (double)dbg[7], (double)dbg[8], (double)dbg[9], (double)dbg[10]);
   }
   return CSDO_OK;
 }

@@ -34,11 +34,19 @@ enum Pl : int { PL_A = 0, PL_B, PL_G, PL_U, PL_E, PL_W, PL_COUNT };
 // local unknown indices inside visit_rows: own step 0..5, next step x,y,yaw,steer 6..9
 enum Var : int { VX = 0, VY, VP, VS, VV, VW, NX, NY, NP, NS };
 
+// band solver geometry (band_solver.cuh)
+constexpr int kMaxP = 16;                 // horizon partitions (lanes of the solver warp)
+constexpr int kMaxNs = 6 * (kMaxP - 1);   // separator unknowns
+constexpr int kL2Tinv = 4 * 18 * 18, kL2R = 18 * 18, kL2B = 6 * 36;  // level-2 inverses and couplings
+constexpr int kL2Doubles = kL2Tinv + kL2R + kL2B;
+constexpr int kSkewPad = 256;  // extra doubles at the end of the L6 area (<= 16 partitions x 14 doubles)
+
 struct BandMem {
   double *L6, *dinv;  // [(6t+k)*6 + d-1], [6t+k]; generic pointers (shared or global)
-  double *Sinv;       // dense inverse of the separator Schur complement (shared)
-  double *sv;         // 3 * kMaxNs scratch: g, x_sep, pivot row (shared)
-  double *G;          // factor-time scratch: per partition GCC[21] GBB[21] GBC[36] (shared)
+  double *Sinv;       // level-2 inverses of the separator system, kL2Doubles (shared)
+  double *sv;         // 3 * kMaxNs scratch: g, x_sep, z / pivot rows (shared)
+  double *G;          // factor-time scratch: per partition GCC[21] GBB[21] GBC[36] = 78 * kMaxP doubles (shared)
+  const int *tab;     // bank-skew table of the partitions (shared context)
 };
 
 // CTA-uniform context of the agent being refined.  It lives in SHARED memory (written by thread 0
@@ -54,6 +62,7 @@ struct CtxShared {
   double *Es;    // Ruiz row scaling of the fixed rows, 16 planes (read-only during the ADMM loop)
   double *ws;    // ADMM row state w = z_hat + y/rho of the fixed rows, 16 planes
   BandMem bm;    // band factor storage (band_solver.cuh)
+  int skew_tab[kMaxP];
   // per-CTA global scratch
   double *cur, *sol, *dy;
   double *pl;    // plane rows of this agent: shared memory when they fit (K <= KS), else global scratch
@@ -137,11 +146,7 @@ __device__ __forceinline__ void block_reduce(double (&v)[N], double *red) {
 template <class F>
 __device__ __forceinline__ void visit_rows(Ctx &c, const csdo_params &P, F &f) {
   const int t = c.t();
-  __builtin_assume(__isShared(c.ros()));
-  __builtin_assume(__isShared(c.cfgs()));
-  __builtin_assume(__isShared(c.Es()));
-  __builtin_assume(__isShared(c.ws()));
-  __builtin_assume(__isShared(c.pstart()));
+  __builtin_assume(__isShared(c.pstart()));  // (row data, E and w may live in global scratch: generic loads)
   const int NTs = c.NT();
   double ro[RO_COUNT], E[13], w[13];
   {

@@ -544,7 +544,7 @@ __device__ __forceinline__ void form_and_factor(Ctx &c, const csdo_params &P) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) c.carry()[k * NT + t] = hf.nd[k];
     // clear this step's band rows; the last step's missing v, w are dummy unknowns (H_ii = 1)
-    const int sk0 = make_parts(Nt).skew_of_block(t);
+    const int sk0 = make_parts(Nt, c.s->skew_tab).skew_of_block(t);
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
 #pragma unroll
@@ -555,7 +555,7 @@ __device__ __forceinline__ void form_and_factor(Ctx &c, const csdo_params &P) {
   __syncthreads();
   if (c.active()) {
     const int nv = nvar(c);
-    const Parts pt_ = make_parts(Nt);
+    const Parts pt_ = make_parts(Nt, c.s->skew_tab);
     double dk[10];
     load_xv(c, c.D(), dk);
     // objective (dsqp_solver.cc:163-197): second difference on v, identity on w
@@ -915,14 +915,19 @@ __device__ __forceinline__ void refine_body(const DevBatch &B, const DevOut &O, 
     cs.NT = LY.NT; cs.KP = 4 * LY.KMAX;
     cs.x = smem + LY.o_x; cs.xt = smem + LY.o_xt; cs.rhs = smem + LY.o_rhs; cs.D = smem + LY.o_D;
     cs.carry = smem + LY.o_carry; cs.red = smem + LY.o_red;
-    cs.ros = smem + LY.o_ro; cs.cfgs = cs.ros + RO_COUNT * NT; cs.Es = smem + LY.o_E; cs.ws = smem + LY.o_w;
+    const bool rows_glob = LY.tier & 1;
+    cs.ros = rows_glob ? slot + LY.g_ro : smem + LY.o_ro;
+    cs.cfgs = cs.ros + RO_COUNT * NT;
+    cs.Es = rows_glob ? slot + LY.g_E : smem + LY.o_E;
+    cs.ws = rows_glob ? slot + LY.g_w : smem + LY.o_w;
     cs.pstart = reinterpret_cast<int *>(smem + LY.o_pstart);
-    cs.bm.L6 = LY.tier >= 2 ? slot + LY.g_L : smem + LY.o_L;
+    cs.bm.L6 = (LY.tier & 2) ? slot + LY.g_L : smem + LY.o_L;
     cs.bm.dinv = cs.bm.L6 + 36 * NT + kSkewPad;
-    cs.l_shared = LY.tier < 2;
+    cs.l_shared = !(LY.tier & 2);
     cs.bm.Sinv = smem + LY.o_sinv;
-    cs.bm.sv = cs.bm.Sinv + kMaxNs * kMaxNs;
-    cs.bm.G = cs.xt;  // xt and rhs are contiguous and free while a factorization runs
+    cs.bm.sv = cs.bm.Sinv + kL2Doubles;
+    cs.bm.tab = cs.skew_tab;
+    cs.bm.G = cs.xt;  // xt, rhs and carry are contiguous (16 NT doubles) and free while a factorization runs
     cs.cur = slot + LY.g_cur; cs.sol = slot + LY.g_sol; cs.dy = slot + LY.g_dy;
     cs.pl_glob = slot + LY.g_pl; cs.pl_smem = smem + LY.o_pl; cs.KS = LY.KS;
     cs.fn_solve = reinterpret_cast<void *>(*(volatile BandSolveFn *)&g_band_solve[cs.l_shared ? 1 : 0]);
@@ -958,6 +963,7 @@ __device__ __forceinline__ void refine_body(const DevBatch &B, const DevOut &O, 
     const int64_t off = B.agent_off[a];
     if (threadIdx.x == 0) {
       cs.Nt = Nt;
+      fill_skew_table(Nt, cs.skew_tab);
       cs.K = B.plane_ptr[a + 1] - B.plane_ptr[a];
       cs.pl = cs.K <= cs.KS ? cs.pl_smem : cs.pl_glob;
       cs.plane_t = B.plane_t + B.plane_ptr[a];
@@ -1073,11 +1079,21 @@ dsqp_refine_kernel(const DevBatch B, const DevOut O, const csdo_params P, const 
   refine_body(B, O, P, LY, scratch, queue);
 }
 
+// register-capped variants for one more resident CTA per SM (3 x 96 threads x 224, 2 x 160 x 200)
+template <int MAXREG>
+__global__ void __maxnreg__(MAXREG)
+dsqp_refine_kernel_lean(const DevBatch B, const DevOut O, const csdo_params P, const Layout LY, double *scratch,
+                        int *queue) {
+  refine_body(B, O, P, LY, scratch, queue);
+}
+
 using RefineKernel = void (*)(const DevBatch, const DevOut, const csdo_params, const Layout, double *, int *);
-static RefineKernel pick_kernel(int block) {
+// lean: the variant compiled for one more resident CTA per SM (fewer registers per thread)
+static RefineKernel pick_kernel(int block, bool lean) {
   if (block <= 64) return dsqp_refine_kernel<64, 4>;
-  if (block <= 96) return dsqp_refine_kernel<96, 2>;
+  if (block <= 96) return lean ? dsqp_refine_kernel_lean<224> : dsqp_refine_kernel<96, 2>;
   if (block <= 128) return dsqp_refine_kernel<128, 2>;
+  if (block <= 160 && lean) return dsqp_refine_kernel_lean<200>;
   if (block <= 256) return dsqp_refine_kernel<256, 1>;
   return dsqp_refine_kernel<512, 1>;
 }
@@ -1133,19 +1149,24 @@ __global__ void corridors_kernel(const DevBatch B, const csdo_params P, int doub
 // host-side launchers (called from csdo_api.cpp through dsqp_launch.h)
 // ===================================================================
 Layout make_layout(int NT, int KMAX, int tier, int KS) {
+  // tier bit 0: per-step row data / row scaling / row state in global scratch instead of shared memory
+  // tier bit 1: band factor in global scratch
   Layout l{};
   l.NT = NT; l.KMAX = KMAX; l.tier = tier; l.KS = KS;
+  const bool rows_glob = tier & 1, band_glob = tier & 2;
   int o = 0;
   auto take = [&](int n) { int r = o; o += (n + 1) & ~1; return r; };
-  l.o_x = take(6 * NT); l.o_xt = take(6 * NT); l.o_rhs = take(6 * NT); l.o_D = take(6 * NT);
-  l.o_carry = take(4 * NT);
-  l.o_ro = take(RO_COUNT * NT + 8);
-  l.o_E = take(16 * NT);
-  l.o_w = take(16 * NT);
+  l.o_x = take(6 * NT); l.o_D = take(6 * NT); l.o_xt = take(6 * NT); l.o_rhs = take(6 * NT);
+  l.o_carry = take(4 * NT);  // xt | rhs | carry double as factor-time scratch (78 * kMaxP doubles <= 16 NT for NT >= 96)
+  if (!rows_glob) {
+    l.o_ro = take(RO_COUNT * NT + 8);
+    l.o_E = take(16 * NT);
+    l.o_w = take(16 * NT);
+  }
   l.o_red = take(((NT + 31) / 32 + 1) * N_COUNT);
   l.o_pstart = take((NT + 2 + 1) / 2);
-  l.o_sinv = take(kMaxNs * kMaxNs + 3 * kMaxNs + 8);
-  l.o_L = tier < 2 ? take(kLw * 6 * NT + kSkewPad) : 0;
+  l.o_sinv = take(kL2Doubles + 3 * kMaxNs);
+  l.o_L = band_glob ? 0 : take(kLw * 6 * NT + kSkewPad);
   l.o_pl = take(PL_COUNT * 4 * KS);
   l.smem_doubles = o;
   size_t g = 0;
@@ -1153,14 +1174,15 @@ Layout make_layout(int NT, int KMAX, int tier, int KS) {
   l.g_cur = gtake(6 * (size_t)NT); l.g_sol = gtake(6 * (size_t)NT); l.g_dy = gtake(16 * (size_t)NT);
   l.g_pl = gtake((size_t)PL_COUNT * 4 * KMAX);
   l.g_L = gtake((size_t)kLw * 6 * NT + kSkewPad);
+  l.g_ro = gtake((size_t)RO_COUNT * NT + 8); l.g_E = gtake(16 * (size_t)NT); l.g_w = gtake(16 * (size_t)NT);
   l.slot_doubles = g;
   return l;
 }
 
 cudaError_t launch_refine(const DevBatch &B, const DevOut &O, const csdo_params &P, const Layout &LY,
-                          double *scratch, int *queue, int grid, int block, cudaStream_t stream) {
+                          double *scratch, int *queue, int grid, int block, bool lean, cudaStream_t stream) {
   const int smem = LY.smem_doubles * 8;
-  RefineKernel kern = pick_kernel(block);
+  RefineKernel kern = pick_kernel(block, lean);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   if (const char *co = getenv("CSDO_CARVEOUT"))  // developer knob: shared-memory carve-out in percent
@@ -1183,8 +1205,8 @@ cudaError_t launch_corridors(const DevBatch &B, const csdo_params &P, int double
   return cudaGetLastError();
 }
 
-int refine_occupancy(int block, int smem_bytes) {
-  RefineKernel kern = pick_kernel(block);
+int refine_occupancy(int block, int smem_bytes, bool lean) {
+  RefineKernel kern = pick_kernel(block, lean);
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) return 0;
   int n = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, block, smem_bytes) != cudaSuccess) return 0;
@@ -1197,9 +1219,9 @@ void read_debug_counters(unsigned long long *out16) {
   cudaMemcpyToSymbol(g_dbg, z, sizeof(z));
 }
 
-int refine_kernel_regs(int block) {
+int refine_kernel_regs(int block, bool lean) {
   cudaFuncAttributes fa;
-  if (cudaFuncGetAttributes(&fa, pick_kernel(block)) != cudaSuccess) return -1;
+  if (cudaFuncGetAttributes(&fa, pick_kernel(block, lean)) != cudaSuccess) return -1;
   return fa.numRegs;
 }
 

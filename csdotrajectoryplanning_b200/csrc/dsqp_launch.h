@@ -36,16 +36,16 @@ struct Layout {
   int NT, KMAX, tier, smem_doubles;
   int KS;  // planes per agent that fit the shared-memory plane area
   int o_x, o_xt, o_rhs, o_D, o_carry, o_red, o_pstart, o_L, o_sinv, o_pl, o_ro, o_E, o_w;
-  size_t g_cur, g_sol, g_dy, g_pl, g_L, slot_doubles;
+  size_t g_cur, g_sol, g_dy, g_pl, g_L, g_ro, g_E, g_w, slot_doubles;
 };
 
 Layout make_layout(int NT, int KMAX, int tier, int KS);
-int refine_occupancy(int block, int smem_bytes);
-int refine_kernel_regs(int block);
+int refine_occupancy(int block, int smem_bytes, bool lean);
+int refine_kernel_regs(int block, bool lean);
 void read_debug_counters(unsigned long long *out16);
 
 cudaError_t launch_refine(const DevBatch &B, const DevOut &O, const csdo_params &P, const Layout &LY,
-                          double *scratch, int *queue, int grid, int block, cudaStream_t stream);
+                          double *scratch, int *queue, int grid, int block, bool lean, cudaStream_t stream);
 cudaError_t launch_corridors(const DevBatch &B, const csdo_params &P, int double_centres, double *corridors,
                              int *box_status, int *inst_static_legal, cudaStream_t stream);
 
