@@ -1079,21 +1079,14 @@ dsqp_refine_kernel(const DevBatch B, const DevOut O, const csdo_params P, const 
   refine_body(B, O, P, LY, scratch, queue);
 }
 
-// register-capped variants for one more resident CTA per SM (3 x 96 threads x 224, 2 x 160 x 200)
-template <int MAXREG>
-__global__ void __maxnreg__(MAXREG)
-dsqp_refine_kernel_lean(const DevBatch B, const DevOut O, const csdo_params P, const Layout LY, double *scratch,
-                        int *queue) {
-  refine_body(B, O, P, LY, scratch, queue);
-}
-
 using RefineKernel = void (*)(const DevBatch, const DevOut, const csdo_params, const Layout, double *, int *);
-// lean: the variant compiled for one more resident CTA per SM (fewer registers per thread)
+// lean: the variant compiled for one more resident CTA per SM.  Registers are allocated per SM
+// sub-partition (16384 each): 9 or 10 resident warps put 3 on one sub-partition, i.e. <= 168 per thread.
 static RefineKernel pick_kernel(int block, bool lean) {
   if (block <= 64) return dsqp_refine_kernel<64, 4>;
-  if (block <= 96) return lean ? dsqp_refine_kernel_lean<224> : dsqp_refine_kernel<96, 2>;
+  if (block <= 96) return lean ? dsqp_refine_kernel<96, 3> : dsqp_refine_kernel<96, 2>;
   if (block <= 128) return dsqp_refine_kernel<128, 2>;
-  if (block <= 160 && lean) return dsqp_refine_kernel_lean<200>;
+  if (block <= 160 && lean) return dsqp_refine_kernel<160, 2>;
   if (block <= 256) return dsqp_refine_kernel<256, 1>;
   return dsqp_refine_kernel<512, 1>;
 }
