@@ -35,10 +35,18 @@
 
 namespace csdo {
 
-__device__ unsigned long long g_dbg[16];  // developer counters (CSDO_PROFILE)
+// developer counters: cycle timers of the factor / solve parts, compiled in with -DCSDO_DEV_TIMERS
+// (make DEV=-DCSDO_DEV_TIMERS) and printed by csdo_refine when CSDO_PROFILE is set
+__device__ unsigned long long g_dbg[16];
+#ifdef CSDO_DEV_TIMERS
 #define DBG_T(i) do { if (lane == 0) { long long t_ = clock64(); atomicAdd(&g_dbg[i], (unsigned long long)(t_ - dbg_t0)); dbg_t0 = t_; } } while (0)
-
 #define DBG_TB(i) do { if (lane == 0) { long long t_ = clock64(); atomicAdd(&g_dbg[i], (unsigned long long)(t_ - dbg_t0b)); dbg_t0b = t_; } } while (0)
+#define DBG_CLOCK() clock64()
+#else
+#define DBG_T(i) do { (void)dbg_t0; } while (0)
+#define DBG_TB(i) do { (void)dbg_t0b; } while (0)
+#define DBG_CLOCK() 0ll
+#endif
 
 struct Parts {
   int P, base, rem;
@@ -326,7 +334,7 @@ __device__ __noinline__ void band_factor_warp(const BandMem bm, int Nt) {
   __builtin_assume(__isShared(bm.tab));
   const Parts pt = make_parts(Nt, bm.tab);
   const int lane = threadIdx.x & 31;
-  long long dbg_t0 = clock64();
+  long long dbg_t0 = DBG_CLOCK();
   if (lane < pt.P)
     interior_factor(bm.L6 + (pt.P == 1 ? 0 : pt.skew(lane)), bm.dinv, pt.start(lane), pt.start(lane) + pt.len(lane));
   __syncwarp();
@@ -340,7 +348,7 @@ __device__ __noinline__ void band_factor_warp(const BandMem bm, int Nt) {
   const Lvl2 l2 = make_lvl2(pt.P);
   const int Ps = pt.P - 1, nb = l2.nb, n_g = l2.n_g(), nR = l2.n_r();
   double *Tinv = bm.Sinv, *R = bm.Sinv + kL2Tinv, *Bc = R + kL2R;
-  long long dbg_t0b = clock64();
+  long long dbg_t0b = DBG_CLOCK();
   for (int e = lane; e < 4 * n_g * n_g; e += 32) Tinv[e] = 0.0;
   for (int e = lane; e < nR * nR; e += 32) R[e] = 0.0;
   __syncwarp();
@@ -505,11 +513,12 @@ __device__ __forceinline__ void lvl2_solve(const BandMem &bm, int lane) {
 
 // ---- solve H x = b: b in `rhs` (SoA, overwritten by x), `tmp` is a scratch vector; one warp ----
 template <bool SH>
-__device__ __noinline__ void band_solve_warp(const BandMem bm, double *rhs, double *tmp, int Nt, int NT) {
+__device__ __forceinline__ void band_solve_body(const BandMem bm, double *rhs, double *tmp, int Nt, int NT) {
   if (SH) { __builtin_assume(__isShared(bm.L6)); __builtin_assume(__isShared(bm.dinv)); }
   __builtin_assume(__isShared(bm.Sinv)); __builtin_assume(__isShared(bm.sv));
   __builtin_assume(__isShared(rhs)); __builtin_assume(__isShared(tmp));
   __builtin_assume(__isShared(bm.tab));
+  long long dbg_t0 = DBG_CLOCK();
   const Parts pt = make_parts(Nt, bm.tab);
   const int lane = threadIdx.x & 31;
   if (pt.P == 1) {
@@ -517,7 +526,7 @@ __device__ __noinline__ void band_solve_warp(const BandMem bm, double *rhs, doub
     __syncwarp();
     return;
   }
-  long long dbg_t0 = clock64();
+  DBG_T(11);
   const int t0 = pt.start(lane < pt.P ? lane : 0), t1 = t0 + pt.len(lane < pt.P ? lane : 0);
   const int sk = pt.skew(lane < pt.P ? lane : 0);
   if (lane < pt.P) interior_solve(bm.L6 + sk, bm.dinv, rhs, tmp, t0, t1, NT);  // S1
@@ -586,6 +595,10 @@ __device__ __noinline__ void band_solve_warp(const BandMem bm, double *rhs, doub
   }
   __syncwarp();
   DBG_T(3);
+}
+template <bool SH>
+__device__ __noinline__ void band_solve_warp(const BandMem bm, double *rhs, double *tmp, int Nt, int NT) {
+  band_solve_body<SH>(bm, rhs, tmp, Nt, NT);
 }
 
 }  // namespace csdo

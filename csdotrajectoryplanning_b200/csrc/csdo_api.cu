@@ -312,7 +312,7 @@ int csdo_refine(csdo_handle *h, const csdo_batch *in, csdo_result *out) {
   if ((rc = download(h, out->inst_status, O.inst_status, I))) return rc;
   if ((rc = download(h, out->inst_static_legal, O.inst_static_legal, I))) return rc;
   if (set_err(h, "refine", cudaStreamSynchronize(h->stream))) return CSDO_ERR_CUDA;
-  if (getenv("CSDO_PROFILE")) {   // developer aid: per-phase cycles of thread 0, summed over CTAs
+  if (getenv("CSDO_PROFILE")) {   // developer aid (needs a -DCSDO_DEV_TIMERS build): per-phase cycles, summed over CTAs
     unsigned long long ph[8];
     cudaMemcpy(ph, static_cast<char *>(h->queue.p) + 8, sizeof(ph), cudaMemcpyDeviceToHost);
     static const char *names[8] = {"corridor", "assemble", "ruiz", "factor", "solve", "rows", "check", "other"};
@@ -323,6 +323,7 @@ int csdo_refine(csdo_handle *h, const csdo_batch *in, csdo_result *out) {
     unsigned long long dbg[16];
     csdo::read_debug_counters(dbg);
     fprintf(stderr, "[csdo profile] solve parts: S1 %.3e  S2 %.3e  Sinv %.3e  S3 %.3e\n", (double)dbg[0], (double)dbg[1], (double)dbg[2], (double)dbg[3]);
+    fprintf(stderr, "[csdo profile] solve entry %.3e  caller-side call time %.3e\n", (double)dbg[11], (double)dbg[12]);
     fprintf(stderr, "[csdo profile] factor parts: F1 %.3e  F2 %.3e  F3 %.3e (scatter %.3e  groups %.3e  R %.3e  Rinv %.3e)\n",
             (double)dbg[4], (double)dbg[5], (double)dbg[6], (double)dbg[7], (double)dbg[8], (double)dbg[9], (double)dbg[10]);
   }

@@ -53,7 +53,7 @@ struct BandMem {
 // between barriers): keeping two dozen pointers per thread in registers starved the row passes.
 struct CtxShared {
   int Nt, NT, K, KP, No, KS, solver_warp;
-  bool l_shared;
+  bool l_shared, rows_glob;
   // shared-memory vectors, SoA with stride NT: v[k*NT + t]
   double *x, *xt, *rhs, *D, *carry, *red;
   int *pstart;   // [Nt+1] first plane of each step
@@ -81,10 +81,12 @@ struct CtxShared {
 struct Ctx {
   CtxShared *s;
   double rho, c;    // current rho and Ruiz cost scaling (every thread holds the same value)
+#ifdef CSDO_DEV_TIMERS
   long long ph[8];  // phase cycle counters (developer profiling)
+#endif
 #define CSDO_GET(type, name) __device__ __forceinline__ type name() const { return s->name; }
   CSDO_GET(int, Nt) CSDO_GET(int, NT) CSDO_GET(int, K) CSDO_GET(int, KP) CSDO_GET(int, No) CSDO_GET(int, KS)
-  CSDO_GET(int, solver_warp) CSDO_GET(bool, l_shared)
+  CSDO_GET(int, solver_warp) CSDO_GET(bool, l_shared) CSDO_GET(bool, rows_glob)
   CSDO_GET(double *, x) CSDO_GET(double *, xt) CSDO_GET(double *, rhs) CSDO_GET(double *, D)
   CSDO_GET(double *, carry) CSDO_GET(double *, red) CSDO_GET(int *, pstart) CSDO_GET(double *, ros)
   CSDO_GET(double *, cfgs) CSDO_GET(double *, Es) CSDO_GET(double *, ws)
@@ -149,12 +151,21 @@ __device__ __forceinline__ void visit_rows(Ctx &c, const csdo_params &P, F &f) {
   __builtin_assume(__isShared(c.pstart()));  // (row data, E and w may live in global scratch: generic loads)
   const int NTs = c.NT();
   double ro[RO_COUNT], E[13], w[13];
+  const bool rows_glob = c.rows_glob();
   {
     const double *ro_ = c.ros() + t, *Ep = c.Es() + t, *wp = c.ws() + t;
+    if (rows_glob) {  // global scratch (plain loads: the read-only part is reused from L1 across passes)
 #pragma unroll
-    for (int i = 0; i < RO_COUNT; ++i) ro[i] = ro_[i * NTs];
+      for (int i = 0; i < RO_COUNT; ++i) ro[i] = ro_[i * NTs];
 #pragma unroll
-    for (int i = 0; i < 13; ++i) { E[i] = Ep[i * NTs]; w[i] = wp[i * NTs]; }
+      for (int i = 0; i < 13; ++i) { E[i] = Ep[i * NTs]; w[i] = wp[i * NTs]; }
+    } else {
+      __builtin_assume(__isShared(ro_)); __builtin_assume(__isShared(Ep)); __builtin_assume(__isShared(wp));
+#pragma unroll
+      for (int i = 0; i < RO_COUNT; ++i) ro[i] = ro_[i * NTs];
+#pragma unroll
+      for (int i = 0; i < 13; ++i) { E[i] = Ep[i * NTs]; w[i] = wp[i * NTs]; }
+    }
   }
   const int k0 = c.pstart()[t], k1 = c.pstart()[t + 1];
 #define RO(i) ro[i]
@@ -191,22 +202,30 @@ __device__ __forceinline__ void visit_rows(Ctx &c, const csdo_params &P, F &f) {
 #undef RO
   {
     double *Ep = c.Es() + t, *wp = c.ws() + t;
+    if (rows_glob) {
 #pragma unroll
-    for (int i = 0; i < 13; ++i) {
-      if (F::kWriteW) wp[i * NTs] = w[i];
-      if (F::kWriteE) Ep[i * NTs] = E[i];
+      for (int i = 0; i < 13; ++i) {
+        if (F::kWriteW) wp[i * NTs] = w[i];
+        if (F::kWriteE) Ep[i * NTs] = E[i];
+      }
+    } else {
+      __builtin_assume(__isShared(Ep)); __builtin_assume(__isShared(wp));
+#pragma unroll
+      for (int i = 0; i < 13; ++i) {
+        if (F::kWriteW) wp[i * NTs] = w[i];
+        if (F::kWriteE) Ep[i * NTs] = E[i];
+      }
     }
   }
   // calcInterVehicleConstraint :1097-1129: 4 rows per plane of this step, l = -inf.  One plane = 4 rows
   // = 12 16-byte loads issued together, processed from registers, w and E written back together.
-  // On-chip plane rows use plain shared-memory loads (LDS); overflow rows live in global scratch (L2).
-  const bool on_chip = c.pl() == c.pl_smem();
-  for (int k = k0; k < k1; ++k) {
-    double v[4][PL_COUNT];
-    double2 *q2;
-    if (on_chip) {
-      __builtin_assume(__isShared(c.pl_smem()));
-      q2 = reinterpret_cast<double2 *>(c.pl_smem() + (size_t)PL_COUNT * 4 * k);
+  // On-chip plane rows use plain shared-memory loads (LDS); overflow rows live in global scratch (L2):
+  // there the next plane is fetched while the current one is processed.
+  if (c.pl() == c.pl_smem()) {
+    __builtin_assume(__isShared(c.pl_smem()));
+    for (int k = k0; k < k1; ++k) {
+      double2 *q2 = reinterpret_cast<double2 *>(c.pl_smem() + (size_t)PL_COUNT * 4 * k);
+      double v[4][PL_COUNT];
 #pragma unroll
       for (int r = 0; r < 4; ++r)
 #pragma unroll
@@ -215,28 +234,42 @@ __device__ __forceinline__ void visit_rows(Ctx &c, const csdo_params &P, F &f) {
           v[r][2 * h] = d2.x;
           v[r][2 * h + 1] = d2.y;
         }
-    } else {
-      q2 = reinterpret_cast<double2 *>(c.pl_glob() + (size_t)PL_COUNT * 4 * k);
 #pragma unroll
       for (int r = 0; r < 4; ++r)
+        f.template row<3>(-1, VX, v[r][PL_A], VY, v[r][PL_B], VP, v[r][PL_G], 0, 0.0, -INFINITY, v[r][PL_U],
+                          v[r][PL_W], v[r][PL_E]);
+      if (F::kWriteW || F::kWriteE) {
 #pragma unroll
-        for (int h = 0; h < PL_COUNT / 2; ++h) {
-          const double2 d2 = q2[r * (PL_COUNT / 2) + h];
-          v[r][2 * h] = d2.x;
-          v[r][2 * h + 1] = d2.y;
-        }
+        for (int r = 0; r < 4; ++r) q2[r * (PL_COUNT / 2) + PL_E / 2] = make_double2(v[r][PL_E], v[r][PL_W]);
+      }
     }
+  } else if (k0 < k1) {
+    double2 nx[4 * (PL_COUNT / 2)];
+    {
+      const double2 *q2 = reinterpret_cast<const double2 *>(c.pl_glob() + (size_t)PL_COUNT * 4 * k0);
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
-      f.template row<3>(-1, VX, v[r][PL_A], VY, v[r][PL_B], VP, v[r][PL_G], 0, 0.0, -INFINITY, v[r][PL_U],
-                        v[r][PL_W], v[r][PL_E]);
-    if (F::kWriteW || F::kWriteE) {
-      if (on_chip) {
-        __builtin_assume(__isShared(c.pl_smem()));
-        double2 *s2 = reinterpret_cast<double2 *>(c.pl_smem() + (size_t)PL_COUNT * 4 * k);
+      for (int i = 0; i < 4 * (PL_COUNT / 2); ++i) nx[i] = q2[i];
+    }
+    for (int k = k0; k < k1; ++k) {
+      double2 *q2 = reinterpret_cast<double2 *>(c.pl_glob() + (size_t)PL_COUNT * 4 * k);
+      double v[4][PL_COUNT];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) s2[r * (PL_COUNT / 2) + PL_E / 2] = make_double2(v[r][PL_E], v[r][PL_W]);
-      } else {
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int h = 0; h < PL_COUNT / 2; ++h) {
+          v[r][2 * h] = nx[r * (PL_COUNT / 2) + h].x;
+          v[r][2 * h + 1] = nx[r * (PL_COUNT / 2) + h].y;
+        }
+      if (k + 1 < k1) {
+        const double2 *qn = q2 + 4 * (PL_COUNT / 2);
+#pragma unroll
+        for (int i = 0; i < 4 * (PL_COUNT / 2); ++i) nx[i] = qn[i];
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        f.template row<3>(-1, VX, v[r][PL_A], VY, v[r][PL_B], VP, v[r][PL_G], 0, 0.0, -INFINITY, v[r][PL_U],
+                          v[r][PL_W], v[r][PL_E]);
+      if (F::kWriteW || F::kWriteE) {
 #pragma unroll
         for (int r = 0; r < 4; ++r) q2[r * (PL_COUNT / 2) + PL_E / 2] = make_double2(v[r][PL_E], v[r][PL_W]);
       }

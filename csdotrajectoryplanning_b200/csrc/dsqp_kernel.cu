@@ -592,8 +592,15 @@ __device__ __forceinline__ void form_and_factor(Ctx &c, const csdo_params &P) {
 }
 
 // optional phase timing (thread 0's clock), accumulated per CTA and added to queue[2..] at exit
+#ifdef CSDO_DEV_TIMERS
 #define PH_T0() long long ph_t0 = clock64()
 #define PH_ADD(id) do { const long long ph_t1 = clock64(); c.ph[id] += ph_t1 - ph_t0; ph_t0 = ph_t1; } while (0)
+#define PH_RESET() ph_t0 = clock64()
+#else
+#define PH_T0() do {} while (0)
+#define PH_ADD(id) do {} while (0)
+#define PH_RESET() do {} while (0)
+#endif
 
 struct QpOut {
   int status, iters, n_factor;
@@ -755,7 +762,17 @@ __device__ __forceinline__ QpOut solve_qp(Ctx &c, const csdo_params &P) {
     __syncwarp();  // the solver warp must enter the solve converged (threads leave barriers individually)
     if ((c.tid() >> 5) == c.solver_warp()) {
       BandSolveFn fn = reinterpret_cast<BandSolveFn>(c.s->fn_solve);  // read once per CTA from global, kept in shared
+#ifdef CSDO_DEV_TIMERS
+      const long long tc0 = clock64();
+#endif
+#ifdef CSDO_INLINE_SOLVE
+      if (c.l_shared()) band_solve_body<true>(c.bm(), c.rhs(), c.xt(), Nt, NT);
+      else
+#endif
       fn(c.bm(), c.rhs(), c.xt(), Nt, NT);
+#ifdef CSDO_DEV_TIMERS
+      if ((threadIdx.x & 31) == 0) atomicAdd(&g_dbg[12], (unsigned long long)(clock64() - tc0));
+#endif
 #ifdef CSDO_DOUBLE_SOLVE  // timing experiment: a second, discarded solve right after the first (warm instruction cache)
       PH_ADD(4);
       band_solve_warp<true>(c.bm(), c.xt(), c.xt(), Nt, NT);
@@ -916,6 +933,7 @@ __device__ __forceinline__ void refine_body(const DevBatch &B, const DevOut &O, 
     cs.x = smem + LY.o_x; cs.xt = smem + LY.o_xt; cs.rhs = smem + LY.o_rhs; cs.D = smem + LY.o_D;
     cs.carry = smem + LY.o_carry; cs.red = smem + LY.o_red;
     const bool rows_glob = LY.tier & 1;
+    cs.rows_glob = rows_glob;
     cs.ros = rows_glob ? slot + LY.g_ro : smem + LY.o_ro;
     cs.cfgs = cs.ros + RO_COUNT * NT;
     cs.Es = rows_glob ? slot + LY.g_E : smem + LY.o_E;
@@ -934,7 +952,9 @@ __device__ __forceinline__ void refine_body(const DevBatch &B, const DevOut &O, 
     cs.fn_factor = reinterpret_cast<void *>(*(volatile BandFactorFn *)&g_band_factor[cs.l_shared ? 1 : 0]);
   }
 
+#ifdef CSDO_DEV_TIMERS
   for (int k = 0; k < 8; ++k) c.ph[k] = 0;
+#endif
   // The warp that runs the band factor/solve differs between the CTAs resident on one SM, so that
   // their (single-warp, issue-bound) solves land on different SM sub-partitions (warp id % 4).
   if (threadIdx.x == 0) {
@@ -1019,7 +1039,7 @@ __device__ __forceinline__ void refine_body(const DevBatch &B, const DevOut &O, 
       assemble_rows(c, P);
       PH_ADD(1);
       const QpOut q = solve_qp(c, P);
-      ph_t0 = clock64();
+      PH_RESET();
       status = q.status; admm += q.iters; nfac += q.n_factor;
       double s[1] = {0.0};
       if (c.active()) {
@@ -1066,10 +1086,12 @@ __device__ __forceinline__ void refine_body(const DevBatch &B, const DevOut &O, 
     __syncthreads();
     PH_ADD(7);
   }
+#ifdef CSDO_DEV_TIMERS
   if (threadIdx.x == 32 * c.solver_warp()) {  // lane 0 of the solver warp: it works in every phase
     unsigned long long *prof = reinterpret_cast<unsigned long long *>(queue + 2);
     for (int k = 0; k < 8; ++k) atomicAdd(prof + k, (unsigned long long)c.ph[k]);
   }
+#endif
 }
 
 template <int MAXT, int MINB>
