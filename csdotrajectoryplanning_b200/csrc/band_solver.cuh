@@ -447,7 +447,9 @@ __device__ __forceinline__ void group_matvec(const double *Tinv, const double *v
   }
 }
 
-// x_sep = S^-1 g for 4 groups of NB separators and 3 level-2 separators (g, x_sep, z in bm.sv)
+// x_sep = S^-1 g for 4 groups of NB separators and 3 level-2 separators (g, x_sep, z in bm.sv).
+// Values move between the steps through shared memory: compact code matters here, the solver warp
+// runs this straight-line code once per ADMM iteration and stalls on instruction fetch otherwise.
 template <int NB>
 __device__ __forceinline__ void lvl2_solve(const BandMem &bm, int lane) {
   constexpr int NG = 6 * NB, GS = 6 * (NB + 1);
@@ -456,53 +458,53 @@ __device__ __forceinline__ void lvl2_solve(const BandMem &bm, int lane) {
   // 1. z_G = Tinv_G g_G
   group_matvec<NB>(Tinv, g, z, lane);
   __syncwarp();
-  // 2. level-2 right-hand side r = g_sigma - couplings * z (kept in registers, exchanged by shuffles)
-  double r = 0.0;
-  {
-    const int l18 = lane < 18 ? lane : 0, s = l18 / 6, a = l18 % 6;
+  // 2. level-2 right-hand side r = g_sigma - couplings * z (in place)
+  if (lane < 18) {
+    const int s = lane / 6, a = lane % 6;
     const double *Bl = Bc + (2 * s) * 36, *Br = Bc + (2 * s + 1) * 36;
     const double *zl = z + s * GS + (NG - 6), *zr = z + (s + 1) * GS;
     double r0 = g[s * GS + NG + a], r1 = 0.0;
 #pragma unroll
     for (int cc = 0; cc < 6; ++cc) { r0 = fma(-Bl[a * 6 + cc], zl[cc], r0); r1 = fma(-Br[cc * 6 + a], zr[cc], r1); }
-    r = r0 + r1;
+    g[s * GS + NG + a] = r0 + r1;
   }
+  __syncwarp();
   // 3. level-2 separators: x_sigma = Rinv r
-  double xsig;
-  {
-    const double *Rr = Rinv + (lane < 18 ? lane : 0) * 18;
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+  if (lane < 18) {
+    const double2 *Rr = reinterpret_cast<const double2 *>(Rinv + lane * 18);
+    double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-    for (int b = 0; b < 18; b += 3) {
-      s0 = fma(Rr[b], __shfl_sync(0xffffffffu, r, b), s0);
-      s1 = fma(Rr[b + 1], __shfl_sync(0xffffffffu, r, b + 1), s1);
-      s2 = fma(Rr[b + 2], __shfl_sync(0xffffffffu, r, b + 2), s2);
-    }
-    xsig = (s0 + s1) + s2;
-    if (lane < 18) xs[(lane / 6) * GS + NG + lane % 6] = xsig;
-  }
-  // 4. move the level-2 solution to the groups' right-hand sides (first / last member of a group);
-  //    every lane takes part in the shuffles
-  {
-    const int l24 = lane < 24 ? lane : 0, G = l24 / 6, a = l24 % 6;
-    const int sp = G > 0 ? G - 1 : 0, sn = G < 3 ? G : 0;
-    const double *Bd = Bc + (2 * sp + 1) * 36, *Bu = Bc + (2 * sn) * 36;
-    double d0 = 0.0, d1 = 0.0;
+    for (int s = 0; s < 3; ++s) {
+      const double2 *gv = reinterpret_cast<const double2 *>(g + s * GS + NG);
 #pragma unroll
-    for (int b = 0; b < 6; ++b) {
-      const double xp = __shfl_sync(0xffffffffu, xsig, 6 * sp + b), xn = __shfl_sync(0xffffffffu, xsig, 6 * sn + b);
-      d0 = fma(Bd[a * 6 + b], xp, d0);
-      d1 = fma(Bu[b * 6 + a], xn, d1);
-    }
-    if (G == 0) d0 = 0.0;
-    if (G == 3) d1 = 0.0;
-    if (lane < 24) {
-      if (NB == 1) {
-        g[G * GS + a] -= d0 + d1;
-      } else {
-        if (G > 0) g[G * GS + a] -= d0;
-        if (G < 3) g[G * GS + (NG - 6) + a] -= d1;
+      for (int h = 0; h < 3; ++h) {
+        const double2 rv = Rr[3 * s + h], gg = gv[h];
+        s0 = fma(rv.x, gg.x, s0);
+        s1 = fma(rv.y, gg.y, s1);
       }
+    }
+    xs[(lane / 6) * GS + NG + lane % 6] = s0 + s1;
+  }
+  __syncwarp();
+  // 4. move the level-2 solution to the groups' right-hand sides (first / last member of a group)
+  if (lane < 24) {
+    const int G = lane / 6, a = lane % 6;
+    double d0 = 0.0, d1 = 0.0;
+    if (G > 0) {
+      const double *Bd = Bc + (2 * (G - 1) + 1) * 36, *xv = xs + (G - 1) * GS + NG;
+#pragma unroll
+      for (int b = 0; b < 6; ++b) d0 = fma(Bd[a * 6 + b], xv[b], d0);
+    }
+    if (G < 3) {
+      const double *Bu = Bc + (2 * G) * 36, *xv = xs + G * GS + NG;
+#pragma unroll
+      for (int b = 0; b < 6; ++b) d1 = fma(Bu[b * 6 + a], xv[b], d1);
+    }
+    if (NB == 1) {
+      g[G * GS + a] -= d0 + d1;
+    } else {
+      if (G > 0) g[G * GS + a] -= d0;
+      if (G < 3) g[G * GS + (NG - 6) + a] -= d1;
     }
   }
   __syncwarp();

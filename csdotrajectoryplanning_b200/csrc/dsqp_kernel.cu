@@ -1105,12 +1105,16 @@ using RefineKernel = void (*)(const DevBatch, const DevOut, const csdo_params, c
 // lean: the variant compiled for one more resident CTA per SM.  Registers are allocated per SM
 // sub-partition (16384 each): 9 or 10 resident warps put 3 on one sub-partition, i.e. <= 168 per thread.
 static RefineKernel pick_kernel(int block, bool lean) {
+#ifdef CSDO_DEV_FAST  // developer builds: only the two 96-thread variants (short compile)
+  return lean ? dsqp_refine_kernel<96, 3> : dsqp_refine_kernel<96, 2>;
+#else
   if (block <= 64) return dsqp_refine_kernel<64, 4>;
   if (block <= 96) return lean ? dsqp_refine_kernel<96, 3> : dsqp_refine_kernel<96, 2>;
   if (block <= 128) return dsqp_refine_kernel<128, 2>;
   if (block <= 160 && lean) return dsqp_refine_kernel<160, 2>;
   if (block <= 256) return dsqp_refine_kernel<256, 1>;
   return dsqp_refine_kernel<512, 1>;
+#endif
 }
 
 // status aggregation of SolverDSQP (dsqp_solver.cc:1224-1243), one thread per instance
