@@ -153,10 +153,18 @@ __device__ __forceinline__ void load_rows(const double *__restrict__ L6, int t, 
     }
 }
 
+// prev_init (optional): solution of the separator block above the partition.  The first block's row
+// slots that reach across the partition boundary hold the raw coupling entries, so starting the forward
+// sweep from it subtracts coupling * x_sep from the right-hand side on the fly.
 __device__ __forceinline__ void interior_solve(const double *__restrict__ L6, const double *__restrict__ dinv,
-                                               const double *in, double *out, int t0, int t1, int NT) {
+                                               const double *in, double *out, int t0, int t1, int NT,
+                                               const double *prev_init = nullptr) {
   // forward: L y = b, stores y * dinv
   double prev[6] = {0, 0, 0, 0, 0, 0};
+  if (prev_init) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) prev[k] = prev_init[k];
+  }
   for (int t = t0; t < t1; ++t) {
     double Lr[6][6], p[6], dv[6];
     load_rows(L6, t, Lr);
@@ -571,17 +579,6 @@ __device__ __forceinline__ void band_solve_body(const BandMem bm, double *rhs, d
   DBG_T(2);
   for (int e = lane; e < Ns; e += 32) rhs[(e % 6) * NT + pt.sep(e / 6)] = xs[e];
   if (lane < pt.P) {  // S3: interiors with the separator solution moved to the right-hand side
-    if (lane > 0) {  // rows of the first block couple to the previous separator
-      const double *xp = xs + 6 * (lane - 1);
-#pragma unroll
-      for (int k = 0; k < 6; ++k) {
-        double a = rhs[k * NT + t0];
-#pragma unroll
-        for (int kc = 0; kc < 6; ++kc)
-          if (kc >= k) a = fma(-coupling(bm.L6 + sk, t0, k, kc), xp[kc], a);
-        rhs[k * NT + t0] = a;
-      }
-    }
     if (lane < pt.P - 1) {  // columns of the last block couple to the next separator's rows
       const double *xn = xs + 6 * lane;
 #pragma unroll
@@ -593,7 +590,8 @@ __device__ __forceinline__ void band_solve_body(const BandMem bm, double *rhs, d
         rhs[kc * NT + t1 - 1] = a;
       }
     }
-    interior_solve(bm.L6 + sk, bm.dinv, rhs, rhs, t0, t1, NT);
+    // (the coupling of the first block to the previous separator rides on the forward sweep)
+    interior_solve(bm.L6 + sk, bm.dinv, rhs, rhs, t0, t1, NT, lane > 0 ? xs + 6 * (lane - 1) : nullptr);
   }
   __syncwarp();
   DBG_T(3);

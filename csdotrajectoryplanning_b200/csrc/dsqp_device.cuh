@@ -139,8 +139,9 @@ __device__ __forceinline__ void block_reduce(double (&v)[N], double *red) {
 }
 
 // ---- the rows of time step t (reference sqp/dsqp_solver.cc:646-1129) ----
-// f.row<NC>(rid, i0,c0,i1,c1,i2,c2,i3,c3, l, u, w, E): row id (0..15 fixed rows, -1 plane rows),
-// NC coefficients on local unknowns i*, raw bounds l,u, the row's ADMM state w and Ruiz factor E.
+// f.row<NC, EQ>(rid, i0,c0,i1,c1,i2,c2,i3,c3, l, u, w, E): row id (0..15 fixed rows, -1 plane rows),
+// NC coefficients on local unknowns i*, raw bounds l,u (EQ: l == u by construction), the row's ADMM
+// state w and Ruiz factor E.
 // A functor declares which of w / E it modifies (kWriteW / kWriteE).  The per-step row data, E and w
 // of the 13 every-step rows are read into registers up front and written back once at the end: with
 // the values behind shared-memory references the compiler had to keep every load behind the previous
@@ -172,18 +173,18 @@ __device__ __forceinline__ void visit_rows(Ctx &c, const csdo_params &P, F &f) {
   const double sn = RO(RO_SN), cs = RO(RO_CS);
   if (c.has_next()) {
     // calcKineConstraint :646-744, lb = ub = -C
-    f.template row<4>(0, VX, 1.0, VP, RO(RO_A1), VV, P.dt * cs, NX, -1.0, RO(RO_KR0), RO(RO_KR0), w[0], E[0]);
-    f.template row<4>(1, VY, 1.0, VP, RO(RO_A2), VV, P.dt * sn, NY, -1.0, RO(RO_KR1), RO(RO_KR1), w[1], E[1]);
-    f.template row<4>(2, VP, 1.0, VS, RO(RO_A3), VV, RO(RO_B3), NP, -1.0, RO(RO_KR2), RO(RO_KR2), w[2], E[2]);
-    f.template row<3>(3, VS, 1.0, VW, P.dt * 1.0, NS, -1.0, 0, 0.0, -0.0, -0.0, w[3], E[3]);
+    f.template row<4, true>(0, VX, 1.0, VP, RO(RO_A1), VV, P.dt * cs, NX, -1.0, RO(RO_KR0), RO(RO_KR0), w[0], E[0]);
+    f.template row<4, true>(1, VY, 1.0, VP, RO(RO_A2), VV, P.dt * sn, NY, -1.0, RO(RO_KR1), RO(RO_KR1), w[1], E[1]);
+    f.template row<4, true>(2, VP, 1.0, VS, RO(RO_A3), VV, RO(RO_B3), NP, -1.0, RO(RO_KR2), RO(RO_KR2), w[2], E[2]);
+    f.template row<3, true>(3, VS, 1.0, VW, P.dt * 1.0, NS, -1.0, 0, 0.0, -0.0, -0.0, w[3], E[3]);
   }
   // calcCfgConstraint :746-788 (cfg = x0,xN,y0,yN,yaw0,yawN); rows 13..15 of the first/last step
   if (t == 0 || t == c.Nt() - 1) {
     const int e = (t == 0) ? 0 : 1;
     double *wc = c.ws() + 13 * NTs + t, *Ec = c.Es() + 13 * NTs + t;
-    f.template row<1>(13, VX, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, c.cfgs()[0 + e], c.cfgs()[0 + e], wc[0], Ec[0]);
-    f.template row<1>(14, VY, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, c.cfgs()[2 + e], c.cfgs()[2 + e], wc[NTs], Ec[NTs]);
-    f.template row<1>(15, VP, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, c.cfgs()[4 + e], c.cfgs()[4 + e], wc[2 * NTs], Ec[2 * NTs]);
+    f.template row<1, true>(13, VX, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, c.cfgs()[0 + e], c.cfgs()[0 + e], wc[0], Ec[0]);
+    f.template row<1, true>(14, VY, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, c.cfgs()[2 + e], c.cfgs()[2 + e], wc[NTs], Ec[NTs]);
+    f.template row<1, true>(15, VP, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, c.cfgs()[4 + e], c.cfgs()[4 + e], wc[2 * NTs], Ec[2 * NTs]);
   }
   // calcCorridorConstraint :874-968: D = [I,0,-f2x sin; 0,I,f2x cos; I,0,-r2x sin; 0,I,r2x cos]
   f.template row<2>(4, VX, 1.0, VP, -P.f2x * sn, 0, 0.0, 0, 0.0, RO(RO_CL0), RO(RO_CU0), w[4], E[4]);

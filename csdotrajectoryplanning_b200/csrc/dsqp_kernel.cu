@@ -261,29 +261,30 @@ struct StepF {
   bool store_dy;
   double *dy_base;  // delta_y of this thread's fixed rows (only kept when the agent has no planes)
   int dy_stride;
-  template <int NC>
+  template <int NC, bool EQ = false>
   __device__ __forceinline__ void row(int rid, int i0, double c0, int i1, double c1, int i2, double c2, int i3,
                                       double c3, double l, double u, double &w, double &E) {
     const double e = E;
-    const double ls = e * l, us = e * u;
-    const double rho_i = row_rho(ls, us, rho);
+    const double ls = e * l, us = EQ ? ls : e * u;
+    // equality rows: us - ls == 0 < kRhoTol and clip(v, ls, ls) == ls for every v
+    const double rho_i = EQ ? kRhoEqOverIneq * rho : row_rho(ls, us, rho);
     double wn, zn;
     if (MODE == 0) {
       wn = e * row_dot<NC>(xv, i0, c0, i1, c1, i2, c2, i3, c3);
       zn = wn;
     } else if (MODE == 3) {
-      const double wo = w, z = clipd(wo, ls, us);
-      const double rho_i_old = row_rho(ls, us, rho_old);
+      const double wo = w, z = EQ ? ls : clipd(wo, ls, us);
+      const double rho_i_old = EQ ? kRhoEqOverIneq * rho_old : row_rho(ls, us, rho_old);
       wn = z + (rho_i_old / rho_i) * (wo - z);
       zn = z;
     } else {
       const double zt = e * row_dot<NC>(xv, i0, c0, i1, c1, i2, c2, i3, c3);
       const double wo = w;
-      const double zo = (MODE == 1) ? wo : clipd(wo, ls, us);
+      const double zo = (MODE == 1) ? wo : (EQ ? ls : clipd(wo, ls, us));
       const double yor = wo - zo;  // y_prev / rho
       const double zhat = alpha * zt + (1.0 - alpha) * zo;
       wn = zhat + yor;
-      zn = clipd(wn, ls, us);
+      zn = EQ ? ls : clipd(wn, ls, us);
       if (store_dy && rid >= 0) dy_base[rid * dy_stride] = rho_i * (zhat - zn);
     }
     w = wn;
@@ -310,7 +311,7 @@ struct CheckF {
   bool with_dy;
   const double *dy_base;
   int dy_stride;
-  template <int NC>
+  template <int NC, bool EQ = false>
   __device__ __forceinline__ void row(int rid, int i0, double c0, int i1, double c1, int i2, double c2, int i3,
                                       double c3, double l, double u, double &w, double &E) {
     const double e = E, einv = 1.0 / e;
@@ -341,7 +342,7 @@ struct ScaleF {
   static constexpr bool kWriteW = false, kWriteE = true;
   double dv[10];    // current D of the touched unknowns
   double cmax[10];  // max_i E_i |a_ij| per touched unknown (without D_j)
-  template <int NC>
+  template <int NC, bool EQ = false>
   __device__ __forceinline__ void row(int rid, int i0, double c0, int i1, double c1, int i2, double c2, int i3,
                                       double c3, double l, double u, double &w, double &E) {
     const double e = E;
@@ -358,7 +359,7 @@ struct ScaleF {
 // reset E to 1 before scaling
 struct ResetF {
   static constexpr bool kWriteW = true, kWriteE = true;
-  template <int NC>
+  template <int NC, bool EQ = false>
   __device__ __forceinline__ void row(int, int, double, int, double, int, double, int, double, double, double,
                                       double &w, double &E) {
     E = 1.0;
@@ -380,7 +381,7 @@ struct HasmF {
     else if (j < 6) cr[i - 6][j] += v;
     else nd[i - 6] += v;  // only i == j occurs
   }
-  template <int NC>
+  template <int NC, bool EQ = false>
   __device__ __forceinline__ void row(int rid, int i0, double c0, int i1, double c1, int i2, double c2, int i3,
                                       double c3, double l, double u, double &w, double &E) {
     const double e = E;
