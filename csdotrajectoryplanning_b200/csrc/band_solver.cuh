@@ -544,16 +544,34 @@ __device__ __forceinline__ void band_solve_body(const BandMem bm, double *rhs, d
   DBG_T(0);
   const int Ns = 6 * (pt.P - 1);
   double *g = bm.sv, *xs = bm.sv + kMaxNs, *z = bm.sv + 2 * kMaxNs;
-  for (int e = lane; e < Ns; e += 32) {  // S2: separator right-hand side
-    const int j = e / 6, k = e % 6, T = pt.sep(j);
-    double s = rhs[k * NT + T];
+  // S2: separator right-hand side g_j = b_T - H[T][T-1] z_{T-1} - H[T][T+1] z_{T+1}, T = sep(j).
+  // Lane p first writes b - (coupling to the last block of ITS partition) for the separator below it,
+  // then subtracts the coupling to the first block of its partition from the separator above it.
+  if (lane < pt.P - 1) {
+    const double *Ls = bm.L6 + sk;  // separator t1 shares the skew of partition `lane`
 #pragma unroll
-    for (int kc = 0; kc < 6; ++kc)
-      if (kc >= k) s = fma(-coupling(bm.L6 + pt.skew(j), T, k, kc), tmp[kc * NT + T - 1], s);
+    for (int k = 0; k < 6; ++k) {
+      double s = rhs[k * NT + t1];
 #pragma unroll
-    for (int kr = 0; kr < 6; ++kr)
-      if (kr <= k) s = fma(-coupling(bm.L6 + pt.skew(j + 1), T + 1, kr, k), tmp[kr * NT + T + 1], s);
-    g[e] = s;
+      for (int kc = 0; kc < 6; ++kc)
+        if (kc >= k) s = fma(-coupling(Ls, t1, k, kc), tmp[kc * NT + t1 - 1], s);
+      g[6 * lane + k] = s;
+    }
+  }
+  __syncwarp();
+  if (lane > 0 && lane < pt.P) {
+    const double *Lp = bm.L6 + sk;
+    double zf[6];
+#pragma unroll
+    for (int kr = 0; kr < 6; ++kr) zf[kr] = tmp[kr * NT + t0];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      double s = g[6 * (lane - 1) + k];
+#pragma unroll
+      for (int kr = 0; kr < 6; ++kr)
+        if (kr <= k) s = fma(-coupling(Lp, t0, kr, k), zf[kr], s);
+      g[6 * (lane - 1) + k] = s;
+    }
   }
   __syncwarp();
   DBG_T(1);
