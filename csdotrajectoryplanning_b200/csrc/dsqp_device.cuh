@@ -115,8 +115,11 @@ __device__ __forceinline__ double clipd(double v, double lo, double hi) {
 }
 
 // ---- block reductions (deterministic): N running values per thread ----
+// red: ((blockDim/32) + 1) * N doubles of shared memory.  Warp partials by shuffles, then thread i < N
+// folds the partials of value i in warp order (compact code: this runs rarely and is fetch-bound).
 template <int N, bool IS_MAX>
 __device__ __forceinline__ void block_reduce(double (&v)[N], double *red) {
+  __builtin_assume(__isShared(red));
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
 #pragma unroll
   for (int i = 0; i < N; ++i) {
@@ -129,12 +132,15 @@ __device__ __forceinline__ void block_reduce(double (&v)[N], double *red) {
     if (lane == 0) red[warp * N + i] = a;
   }
   __syncthreads();
-#pragma unroll
-  for (int i = 0; i < N; ++i) {
-    double a = red[i];
-    for (int wv = 1; wv < nw; ++wv) a = IS_MAX ? fmax(a, red[wv * N + i]) : a + red[wv * N + i];
-    v[i] = a;
+  if ((int)threadIdx.x < N) {
+    double a = red[threadIdx.x];
+#pragma unroll 1
+    for (int wv = 1; wv < nw; ++wv) a = IS_MAX ? fmax(a, red[wv * N + threadIdx.x]) : a + red[wv * N + threadIdx.x];
+    red[nw * N + threadIdx.x] = a;
   }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < N; ++i) v[i] = red[nw * N + i];
   __syncthreads();
 }
 

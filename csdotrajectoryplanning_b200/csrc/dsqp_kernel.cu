@@ -646,6 +646,7 @@ struct CheckOut {
   double ineq_lhs;
 };
 
+// (a __noinline__ copy shrinks the code but shifts the register allocation of the row pass: no net gain)
 __device__ __forceinline__ void check_rows(Ctx &c, const csdo_params &P, bool with_dy, CheckOut &co) {
   const int NT = c.NT(), t = c.t(), Nt = c.Nt();
   // xt <- D x (the current iterate, not x~)
@@ -1183,7 +1184,7 @@ Layout make_layout(int NT, int KMAX, int tier, int KS) {
     l.o_E = take(16 * NT);
     l.o_w = take(16 * NT);
   }
-  l.o_red = take(((NT + 31) / 32 + 1) * N_COUNT);
+  l.o_red = take((((NT < 64 ? 64 : NT) + 31) / 32 + 1) * N_COUNT);  // one row per warp + the result row
   l.o_pstart = take((NT + 2 + 1) / 2);
   l.o_sinv = take(kL2Doubles + 3 * kMaxNs);
   l.o_L = band_glob ? 0 : take(kLw * 6 * NT + kSkewPad);
