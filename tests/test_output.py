@@ -1,0 +1,54 @@
+"""CPU tests of the solution-file writer/readers (dumpSolutions format,
+inter_agent_cons.cc:413-455, and the status parse of scripts/analysis_result.py:53-101)."""
+import numpy as np
+
+from csdotrajectoryplanning_b200.output import (SolutionStatistics, format_solutions, dump_solutions, load_solutions,
+                                                read_solution_status)
+
+
+def _traj():
+    tr = np.zeros((2, 6, 3))
+    tr[0, 0] = [1.0, 1.70649, 2.4125]
+    tr[0, 1] = [2.0, 2.0005, -0.00049]
+    tr[0, 2] = [0.5, 0.5, 0.5]
+    tr[0, 3] = [0.0, 0.321750554, -0.321750554]
+    tr[0, 4] = [0.8, 0.8, 0.0]
+    tr[0, 5] = [0.07, -0.07, 0.0]
+    tr[1, 0] = [10, 10, 10]
+    return tr
+
+
+def test_format_matches_dump_solutions_layout():
+    txt = format_solutions(_traj(), SolutionStatistics(rt_search=0.25, solver_status=-2, search_status=1))
+    lines = txt.splitlines()
+    assert lines[:12] == ["statistics:", "  cost: -1.000", "  makespan: -1.000", "  flowtime: -1.000", "  runtime: -1.000",
+                          "  runtime_search: 0.250", "  runtime_preprocess: -1.000", "  runtime_optimization: -1.000",
+                          "  runtime_decentralized_optimization: -1.000", "  search_status: 1", "  solver_status: -2",
+                          "schedule:"]
+    assert lines[12] == "  agent0:"
+    # first step: x, y, yaw, steer (scaled by 180/3.14), t, v, omega
+    assert lines[13:20] == ["    - x: 1.000", "      y: 2.000", "      yaw: 0.500", "      steer: 0.000", "      t: 0",
+                            "      v: 0.800", "      omega: 4.013"]
+    # second step: std::fixed rounding of the binary value, steer in pseudo-degrees
+    assert lines[20] == "    - x: 1.706" and lines[23] == "      steer: 18.444"
+    # the last step carries no v / omega (inter_agent_cons.cc:449)
+    last = lines[27:32]
+    assert last == ["    - x: 2.413", "      y: -0.000", "      yaw: 0.500", "      steer: -18.444", "      t: 2"]
+    assert lines[32] == "  agent1:"
+    assert txt.endswith("      t: 2\n")
+
+
+def test_round_trip_and_status_rule(tmp_path):
+    p = str(tmp_path / "sol.yaml")
+    tr = _traj()
+    dump_solutions(p, tr, SolutionStatistics(solver_status=2, rt_preprocess=0.5))
+    back = load_solutions(p)
+    assert back.shape == tr.shape
+    assert np.abs(back[:, :3] - tr[:, :3]).max() <= 5e-4 + 1e-12
+    assert np.abs(back[:, 3] - tr[:, 3]).max() <= 5e-4 / (180 / 3.14) + 1e-12
+    assert np.all(back[:, 4:, -1] == 0)
+    st, ok = read_solution_status(p)
+    assert ok and st.solver_status == 2 and st.rt_preprocess == 0.5 and st.search_status == 2
+    for code, want in ((1, True), (-2, True), (2, True), (3, False), (-3, False), (-7, False)):
+        dump_solutions(p, tr, SolutionStatistics(solver_status=code))
+        assert read_solution_status(p)[1] == want
