@@ -622,11 +622,25 @@ __device__ __forceinline__ void finish_rhs(const Ctx &c, const csdo_params &P, c
   }
 }
 
-template <int MODE>
+// AFTER_SOLVE: x~ sits in rhs (scaled space).  The row pass then forms D x~ of this and the next step
+// itself and does the relaxed x update of its own step on the way (no separate pass, no barrier).
+template <int MODE, bool AFTER_SOLVE = false>
 __device__ __forceinline__ void step_rows(Ctx &c, const csdo_params &P, bool store_dy, double rho_old) {
   StepF<MODE> sf;
   if (c.active()) {
-    load_xv(c, c.xt(), sf.xv);
+    if (AFTER_SOLVE) {
+      const int NT = c.NT(), t = c.t(), nv = nvar(c);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const double xtil = c.rhs()[k * NT + t];
+        sf.xv[k] = c.D()[k * NT + t] * xtil;
+        if (k < nv) c.x()[k * NT + t] = P.alpha * xtil + (1.0 - P.alpha) * c.x()[k * NT + t];
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) sf.xv[6 + k] = c.has_next() ? c.D()[k * NT + t + 1] * c.rhs()[k * NT + t + 1] : 0.0;
+    } else {
+      load_xv(c, c.xt(), sf.xv);
+    }
 #pragma unroll
     for (int k = 0; k < 10; ++k) sf.acc[k] = 0.0;
     sf.alpha = P.alpha; sf.rho = c.rho; sf.rho_old = rho_old;
@@ -635,7 +649,7 @@ __device__ __forceinline__ void step_rows(Ctx &c, const csdo_params &P, bool sto
 #pragma unroll
     for (int k = 0; k < 4; ++k) c.carry()[k * c.NT() + c.t()] = sf.acc[6 + k];
   }
-  __syncthreads();
+  __syncthreads();  // every thread has read its neighbour's x~ before rhs is rebuilt
   finish_rhs(c, P, sf.acc);
   __syncthreads();
 }
@@ -783,21 +797,10 @@ __device__ __forceinline__ QpOut solve_qp(Ctx &c, const csdo_params &P) {
     }
     __syncthreads();
     PH_ADD(4);
-    if (c.active()) {
-      const int nv = nvar(c);
-#pragma unroll
-      for (int k = 0; k < 6; ++k) {
-        if (k >= nv) continue;
-        const double xtil = c.rhs()[k * NT + t], xp = c.x()[k * NT + t];
-        c.x()[k * NT + t] = P.alpha * xtil + (1.0 - P.alpha) * xp;
-        c.xt()[k * NT + t] = c.D()[k * NT + t] * xtil;
-      }
-    }
-    __syncthreads();
     const bool can_check = P.check_termination && (iter % P.check_termination == 0);
     const bool store_dy = keep_dy && (can_check || iter == P.osqp_max_iter);
-    if (iter == 1) step_rows<1>(c, P, store_dy, 0.0);
-    else step_rows<2>(c, P, store_dy, 0.0);
+    if (iter == 1) step_rows<1, true>(c, P, store_dy, 0.0);
+    else step_rows<2, true>(c, P, store_dy, 0.0);
     PH_ADD(5);
     checked = false;
     const bool adapt = P.adaptive_rho && P.adaptive_rho_interval && (iter % P.adaptive_rho_interval == 0);

@@ -147,6 +147,24 @@ def test_ragged_batch_and_edge_sizes(oracle, params, solver):
     _assert_same_refine(ro, rg)
 
 
+@pytest.mark.parametrize("acts,na,size", [((27, 30), 6, 50.0), ((40, 42), 6, 60.0), ((50, 52), 6, 60.0),
+                                          ((80, 80), 3, 100.0), ((135, 140), 2, 100.0)])
+def test_long_horizons_cover_every_kernel_variant(oracle, params, solver, acts, na, size):
+    """Horizons 82..421: 16 partitions with the two-level separator solve, the 96/128/160/256/512-thread
+    kernel variants, row arrays and (for the longest) the band factor in global scratch."""
+    inst = [synthetic_instance(400 + acts[0] + k, size, na, 12, acts, params) for k in range(2)]
+    for ins in inst:
+        ins.plane_t, ins.plane_abc, _ = oracle.instance_planes(params, ins.guess)
+    b = pack_instances(inst)
+    ro, _ = oracle.refine(params, b, linsys=0, nthreads=8)
+    rg = solver.refine(b)
+    # iteration / factorization counts identical; trajectories to 1e-5: an agent with 6 SQP iterations and
+    # 750 ADMM iterations at Nt = 241 moves by 1.5e-6 between the oracle's own two linear-system paths
+    _assert_same_refine(ro, rg, traj_tol=1e-5)
+    info = solver.last_launch()
+    assert info["block"] >= b.inst_nt.max() and info["ctas_per_sm"] >= 1
+
+
 def test_statically_illegal_and_infeasible_agents(oracle, params, solver):
     """An agent starting inside an obstacle square (status bookkeeping, solution0 fallback paths)."""
     ins = synthetic_instance(95, 50.0, 4, 6, (8, 12), params)
