@@ -543,7 +543,7 @@ __device__ __forceinline__ void band_solve_body(const BandMem bm, double *rhs, d
   __syncwarp();
   DBG_T(0);
   const int Ns = 6 * (pt.P - 1);
-  double *g = bm.sv, *xs = bm.sv + kMaxNs, *z = bm.sv + 2 * kMaxNs;
+  double *g = bm.sv, *xs = bm.sv + kMaxNs;
   // S2: separator right-hand side g_j = b_T - H[T][T-1] z_{T-1} - H[T][T+1] z_{T+1}, T = sep(j).
   // Lane p first writes b - (coupling to the last block of ITS partition) for the separator below it,
   // then subtracts the coupling to the first block of its partition from the separator above it.
