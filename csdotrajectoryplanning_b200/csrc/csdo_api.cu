@@ -25,7 +25,7 @@ struct csdo_handle {
   csdo_params P{};
   std::string err;
   int num_sms = 0, smem_limit = 0, smem_limit_sm = 0;
-  DevBuf scratch, queue, step_cnt;
+  DevBuf scratch, queue, step_cnt, pass_buf;
   std::vector<DevBuf> stage;  // staging buffers of the host-pointer entry points
   csdo_launch_info last{};
 };
@@ -179,11 +179,13 @@ int run_refine(csdo_handle *h, const DevBatch &B, const DevOut &O, int max_nt, i
   int rc;
   if ((rc = ensure(h, h->scratch, (size_t)grid * LY.slot_doubles * sizeof(double)))) return rc;
   if ((rc = ensure(h, h->queue, 2048))) return rc;
+  if ((rc = ensure(h, h->pass_buf, refine_pass_bytes(B.n_agents)))) return rc;
+  int launches = 0;
   if (set_err(h, "launch_refine",
               launch_refine(B, O, h->P, LY, static_cast<double *>(h->scratch.p), static_cast<int *>(h->queue.p),
-                            grid, block, lean, stream)))
+                            h->pass_buf.p, grid, block, lean, stream, &launches)))
     return CSDO_ERR_CUDA;
-  h->last.launches = 3;
+  h->last.launches = launches;
   h->last.grid = grid; h->last.block = block; h->last.smem_bytes = LY.smem_doubles * 8;
   h->last.tier = LY.tier; h->last.ctas_per_sm = occ;
   return CSDO_OK;
@@ -248,6 +250,7 @@ void csdo_destroy(csdo_handle *h) {
   if (h->scratch.p) cudaFree(h->scratch.p);
   if (h->queue.p) cudaFree(h->queue.p);
   if (h->step_cnt.p) cudaFree(h->step_cnt.p);
+  if (h->pass_buf.p) cudaFree(h->pass_buf.p);
   cudaStreamDestroy(h->stream);
   delete h;
 }

@@ -8,6 +8,8 @@
 //   isFeasible / updateCorridor     sqp/dsqp_solver.cc:292-420, 818-872
 //   generateBox & co                sqp/corridor.cc:25-324
 #include "dsqp_device.cuh"
+#include <cub/device/device_radix_sort.cuh>
+
 #include "band_solver.cuh"
 #include "dsqp_launch.h"
 #include <cstdlib>
@@ -924,7 +926,7 @@ __device__ __forceinline__ bool is_feasible(Ctx &c, const csdo_params &P) {
 // Register budget follows the block size (one thread per time step): horizons <= 128 run with up to
 // 255 registers (2 CTAs/SM), <= 256 with 255 (1 CTA/SM), longer ones with 128.
 __device__ __forceinline__ void refine_body(const DevBatch &B, const DevOut &O, const csdo_params &P,
-                                            const Layout &LY, double *scratch, int *queue) {
+                                            const Layout &LY, double *scratch, int *queue, const PassState &ST) {
   extern __shared__ double smem[];
   __shared__ int s_agent;
   __shared__ int s_flag;
@@ -976,7 +978,8 @@ __device__ __forceinline__ void refine_body(const DevBatch &B, const DevOut &O, 
     const int qi = s_agent;
     __syncthreads();
     if (qi >= B.n_agents) break;
-    const int a = B.agent_order ? B.agent_order[qi] : qi;
+    const int a = ST.order ? ST.order[qi] : qi;
+    if (ST.pass > 0 && ST.done[a]) continue;  // (uniform: every thread reads the same flag)
     // instance of this agent: last i with inst_agent_ptr[i] <= a
     int lo = 0, hi = B.n_inst;
     while (hi - lo > 1) {
@@ -1007,11 +1010,13 @@ __device__ __forceinline__ void refine_body(const DevBatch &B, const DevOut &O, 
       while (l2 < h2) { const int mid = (l2 + h2) >> 1; if (c.plane_t()[mid] < tt) l2 = mid + 1; else h2 = mid; }
       c.pstart()[tt] = l2;
     }
-    // solution0 and the frozen trust centre (dsqp_solver.cc:56-63); cfg (utils.cc:115-120)
+    // solution0 and the frozen trust centre (dsqp_solver.cc:56-63); cfg (utils.cc:115-120).  Later passes
+    // continue from the iterate the previous pass left in the trajectory output.
+    const bool first_pass = ST.pass == 0;
     if (c.active()) {
 #pragma unroll
       for (int k = 0; k < 6; ++k) {
-        double v = c.guess()[k * Nt + c.t()];
+        double v = first_pass ? c.guess()[k * Nt + c.t()] : traj[k * Nt + c.t()];
         if (k >= 4 && !c.has_next()) v = 0.0;
         c.cur()[k * NT + c.t()] = v;
         c.sol()[k * NT + c.t()] = v;
@@ -1026,26 +1031,34 @@ __device__ __forceinline__ void refine_body(const DevBatch &B, const DevOut &O, 
     }
     if (threadIdx.x == 0) s_flag = 0;
     __syncthreads();
-    // calcCorridors (dsqp_solver.cc:1154) on float disc centres
     PH_T0();
-    if (agent_corridors(c, P, c.guess(), c.guess() + Nt, c.guess() + 2 * Nt, smem + LY.o_x, LY.o_carry - LY.o_x,
-                        false, nullptr))
-      s_flag = 1;
-    __syncthreads();
-    if (threadIdx.x == 0 && s_flag) atomicAnd(&O.inst_static_legal[inst], 0);
-    __syncthreads();
+    if (first_pass) {
+      // calcCorridors (dsqp_solver.cc:1154) on float disc centres
+      if (agent_corridors(c, P, c.guess(), c.guess() + Nt, c.guess() + 2 * Nt, smem + LY.o_x, LY.o_carry - LY.o_x,
+                          false, nullptr))
+        s_flag = 1;
+      __syncthreads();
+      if (threadIdx.x == 0 && s_flag) atomicAnd(&O.inst_static_legal[inst], 0);
+      __syncthreads();
+    }
 
+    // `while (delta > th && iter_count < max_iter)` (dsqp_solver.cc:99-253): the first iteration in
+    // pass 0, the remaining ones in pass 1 (see PassState)
     const double th = P.delta_solution_threshold;
-    double delta = th + 1;
-    int iter_count = 0, status = 1, admm = 0, nfac = 0;
+    const bool run_to_end = ST.pass > 0;
+    int iter_count = first_pass ? 0 : O.sqp_iters[a];
+    int status = first_pass ? 1 : O.status[a];
+    int admm = first_pass ? 0 : O.admm_iters[a], nfac = first_pass ? 0 : O.n_factor[a];
+    int last_admm = 0;
+    bool finished = true;
     __syncthreads();
     PH_ADD(0);
-    while (delta > th && iter_count < P.max_iter) {
+    while (iter_count < P.max_iter) {
       assemble_rows(c, P);
       PH_ADD(1);
       const QpOut q = solve_qp(c, P);
       PH_RESET();
-      status = q.status; admm += q.iters; nfac += q.n_factor;
+      status = q.status; admm += q.iters; nfac += q.n_factor; last_admm = q.iters;
       double s[1] = {0.0};
       if (c.active()) {
         const int nv = nvar(c);
@@ -1054,9 +1067,9 @@ __device__ __forceinline__ void refine_body(const DevBatch &B, const DevOut &O, 
           if (k < nv) { const double d = c.sol()[k * NT + c.t()] - c.cur()[k * NT + c.t()]; s[0] += d * d; }
       }
       block_reduce<1, false>(s, c.red());
-      delta = s[0];
+      const double delta = s[0];
       iter_count++;
-      if (iter_count > P.max_iter / 2 && is_feasible(c, P)) break;
+      if (iter_count > P.max_iter / 2 && is_feasible(c, P)) { finished = true; break; }
       if (c.active())
 #pragma unroll
         for (int k = 0; k < 6; ++k) c.cur()[k * NT + c.t()] = c.sol()[k * NT + c.t()];
@@ -1068,6 +1081,8 @@ __device__ __forceinline__ void refine_body(const DevBatch &B, const DevOut &O, 
         __syncthreads();
         PH_ADD(0);
       }
+      finished = !(delta > th && iter_count < P.max_iter);
+      if (finished || !run_to_end) break;
     }
     // extractSingleSolutionVec2OptRes + per-agent records
     double ob[1] = {0.0};
@@ -1087,6 +1102,8 @@ __device__ __forceinline__ void refine_body(const DevBatch &B, const DevOut &O, 
     if (threadIdx.x == 0) {
       O.status[a] = status; O.sqp_iters[a] = iter_count; O.n_qp[a] = iter_count;
       O.admm_iters[a] = admm; O.n_factor[a] = nfac; O.objective[a] = ob[0];
+      ST.done[a] = finished ? 1 : 0;
+      ST.last_admm[a] = last_admm * Nt;  // sort key of the next pass: what the last QP cost
     }
     __syncthreads();
     PH_ADD(7);
@@ -1102,11 +1119,12 @@ __device__ __forceinline__ void refine_body(const DevBatch &B, const DevOut &O, 
 template <int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
 dsqp_refine_kernel(const DevBatch B, const DevOut O, const csdo_params P, const Layout LY, double *scratch,
-                   int *queue) {
-  refine_body(B, O, P, LY, scratch, queue);
+                   int *queue, const PassState ST) {
+  refine_body(B, O, P, LY, scratch, queue, ST);
 }
 
-using RefineKernel = void (*)(const DevBatch, const DevOut, const csdo_params, const Layout, double *, int *);
+using RefineKernel = void (*)(const DevBatch, const DevOut, const csdo_params, const Layout, double *, int *,
+                              const PassState);
 // lean: the variant compiled for one more resident CTA per SM.  Registers are allocated per SM
 // sub-partition (16384 each): 9 or 10 resident warps put 3 on one sub-partition, i.e. <= 168 per thread.
 static RefineKernel pick_kernel(int block, bool lean) {
@@ -1203,20 +1221,78 @@ Layout make_layout(int NT, int KMAX, int tier, int KS) {
   return l;
 }
 
+// sort keys of a pass: unfinished agents by descending cost of their last QP, finished ones last
+__global__ void pass_keys_kernel(int n, const int *done, const int *last_admm, unsigned *keys, int *vals) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  keys[i] = done[i] ? 0xffffffffu : 0x7fffffffu - (unsigned)last_admm[i];
+  vals[i] = i;
+}
+
+namespace {
+struct PassBuf {  // carved out of one device allocation
+  int *done, *last_admm, *vals_in, *vals_out;
+  unsigned *keys_in, *keys_out;
+  void *cub_tmp;
+  size_t cub_bytes;
+};
+size_t cub_sort_bytes(int n) {
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const unsigned *)nullptr, (unsigned *)nullptr, (const int *)nullptr,
+                                  (int *)nullptr, n);
+  return bytes;
+}
+PassBuf carve_pass_buf(void *base, int n) {
+  PassBuf pb;
+  const size_t A = ((size_t)n + 63) & ~(size_t)63;
+  int *p = static_cast<int *>(base);
+  pb.done = p; pb.last_admm = p + A; pb.vals_in = p + 2 * A; pb.vals_out = p + 3 * A;
+  pb.keys_in = reinterpret_cast<unsigned *>(p + 4 * A); pb.keys_out = reinterpret_cast<unsigned *>(p + 5 * A);
+  pb.cub_tmp = p + 6 * A;
+  pb.cub_bytes = cub_sort_bytes(n);
+  return pb;
+}
+}  // namespace
+
+size_t refine_pass_bytes(int n_agents) {
+  const size_t A = ((size_t)n_agents + 63) & ~(size_t)63;
+  return 6 * A * sizeof(int) + cub_sort_bytes(n_agents) + 256;
+}
+
 cudaError_t launch_refine(const DevBatch &B, const DevOut &O, const csdo_params &P, const Layout &LY,
-                          double *scratch, int *queue, int grid, int block, bool lean, cudaStream_t stream) {
+                          double *scratch, int *queue, void *pass_buf, int grid, int block, bool lean,
+                          cudaStream_t stream, int *n_launches) {
   const int smem = LY.smem_doubles * 8;
   RefineKernel kern = pick_kernel(block, lean);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   if (const char *co = getenv("CSDO_CARVEOUT"))  // developer knob: shared-memory carve-out in percent
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(co));
-  e = cudaMemsetAsync(queue, 0, 2048, stream);
-  if (e != cudaSuccess) return e;
-  const int fb = 256;
+  const int fb = 256, n = B.n_agents;
+  int launches = 0;
   fill_int_kernel<<<(B.n_inst + fb - 1) / fb, fb, 0, stream>>>(O.inst_static_legal, B.n_inst, 1);
-  kern<<<grid, block, smem, stream>>>(B, O, P, LY, scratch, queue);
+  ++launches;
+  const PassBuf pb = carve_pass_buf(pass_buf, n);
+  const int passes = P.max_iter > 1 ? 2 : 1;
+  for (int pass = 0; pass < passes; ++pass) {
+    PassState st{pass, pb.done, pb.last_admm, B.agent_order};
+    if (pass > 0) {
+      pass_keys_kernel<<<(n + fb - 1) / fb, fb, 0, stream>>>(n, pb.done, pb.last_admm, pb.keys_in, pb.vals_in);
+      size_t bytes = pb.cub_bytes;
+      e = cub::DeviceRadixSort::SortPairs(pb.cub_tmp, bytes, pb.keys_in, pb.keys_out, pb.vals_in, pb.vals_out, n, 0, 32,
+                                          stream);
+      if (e != cudaSuccess) return e;
+      st.order = pb.vals_out;
+      launches += 2;  // (+ the sort's own kernels)
+    }
+    e = cudaMemsetAsync(queue, 0, 2048, stream);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, block, smem, stream>>>(B, O, P, LY, scratch, queue, st);
+    ++launches;
+  }
   aggregate_status_kernel<<<(B.n_inst + fb - 1) / fb, fb, 0, stream>>>(B, O);
+  ++launches;
+  if (n_launches) *n_launches = launches;
   return cudaGetLastError();
 }
 
