@@ -299,7 +299,10 @@ def main():
                 "hbm": {"bound": "hbm", "achieved": by / kern_s * 1e-9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": by / kern_s * 1e-9 / hbm_peak, "algorithmic_bytes_per_launch": by,
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)"},
-                "note": "banded FP64 ADMM with the working set in shared memory: neither HBM nor tensor cores bind it"}
+                "launches_per_step": 2,
+                "note": "banded FP64 ADMM with the working set in shared memory: neither HBM nor tensor cores bind it; "
+                        "one step = two launches of dsqp_refine_kernel (first SQP iteration of every agent, then the "
+                        "rest in cost-sorted order): flops, bytes, traffic and time are per step"}
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:   # the CPU baseline is reported at N = 1 only
@@ -322,7 +325,7 @@ def main():
                        "admm_iters_per_step_rank0": int(res.admm_iters.sum()),
                        "horizon_max": int(batch.inst_nt.max()), "l2": "256 MiB buffer written between timed iterations",
                        "parallelism": f"instance-sharded x{world}, no data-path collective", "launch": launch},
-            "clocks": clk, "gpu_launches": 3 * args.steps,
+            "clocks": clk, "gpu_launches": int(launch.get("launches", 0)) * args.steps,
             "e2e": {"value": tot_qp / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * t_e2e / args.steps, "matches_device_arm": e2e_ok,
                     "timing": "wall clock around the blocking csdo_refine() calls (pinned host buffers)"},

@@ -4,7 +4,7 @@ usage: python scripts/summarize_profiles.py <round tag, e.g. r01>
   gpurun_out/<tag>_launches.csv        (ncu --metrics gpu__time_duration.sum ... python bench.py ...)
   gpurun_out/<tag>_refine_full.ncu-rep (ncu --set full -k regex:dsqp_refine ... python bench.py ...)
 """
-import collections, csv, io, json, subprocess, sys
+import collections, csv, io, json, os, subprocess, sys
 
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
 rows = list(csv.reader(open(f"gpurun_out/{tag}_launches.csv")))
@@ -36,9 +36,12 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 summ = {a: (c, b) for a, b, c in zip(rr[0], rr[1], rr[2]) if a in want}
 mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 tr = sum(float(summ[k][0].replace(",", "")) * mult[summ[k][1]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
-json.dump({"dram_bytes_per_launch": tr, "source": f"profiles/{tag}_refine_full_summary.txt (ncu --set full, bench workload: 600 instances / 9000 agents)"},
+if os.path.exists("profiles/traffic.json") and "per_pass" in json.load(open("profiles/traffic.json")):
+    print("profiles/traffic.json holds a per-step (two-pass) figure: left unchanged")
+else:
+  json.dump({"dram_bytes_per_launch": tr, "source": f"profiles/{tag}_refine_full_summary.txt (ncu --set full, bench workload: 600 instances / 9000 agents)"},
           open("profiles/traffic.json", "w"))
 open(f"profiles/{tag}_refine_full_summary.txt", "w").write(
-    "# ncu --set full --clock-control none -k regex:dsqp_refine -s 3 -c 1 python bench.py --steps 1 --warmup 1 --no-cpu-baseline\n"
+    "# ncu --set full --clock-control none -k regex:dsqp_refine -s 1 -c 1 python bench.py --steps 1 --warmup 0 --no-cpu-baseline\n# (the second of the two dsqp_refine_kernel launches of a step: the cost-sorted run-to-completion pass)\n"
     + "\n".join(f"{k} = {summ[k][0]} {summ[k][1]}" for k in want if k in summ) + f"\ndram_bytes_per_launch = {tr:.0f}\n")
 print(open(f"profiles/{tag}_refine_full_summary.txt").read())
