@@ -299,10 +299,10 @@ def main():
                 "hbm": {"bound": "hbm", "achieved": by / kern_s * 1e-9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": by / kern_s * 1e-9 / hbm_peak, "algorithmic_bytes_per_launch": by,
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)"},
-                "launches_per_step": 2,
+                "launches_per_step": 1,
                 "note": "banded FP64 ADMM with the working set in shared memory: neither HBM nor tensor cores bind it; "
-                        "one step = two launches of dsqp_refine_kernel (first SQP iteration of every agent, then the "
-                        "rest in cost-sorted order): flops, bytes, traffic and time are per step"}
+                        "one step = one persistent launch of dsqp_refine_kernel (agents re-enqueue themselves after "
+                        "each SQP iteration)"}
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:   # the CPU baseline is reported at N = 1 only

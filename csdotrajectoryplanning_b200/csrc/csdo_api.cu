@@ -179,7 +179,7 @@ int run_refine(csdo_handle *h, const DevBatch &B, const DevOut &O, int max_nt, i
   int rc;
   if ((rc = ensure(h, h->scratch, (size_t)grid * LY.slot_doubles * sizeof(double)))) return rc;
   if ((rc = ensure(h, h->queue, 2048))) return rc;
-  if ((rc = ensure(h, h->pass_buf, refine_pass_bytes(B.n_agents)))) return rc;
+  if ((rc = ensure(h, h->pass_buf, refine_queue_bytes(B.n_agents, h->P)))) return rc;
   int launches = 0;
   if (set_err(h, "launch_refine",
               launch_refine(B, O, h->P, LY, static_cast<double *>(h->scratch.p), static_cast<int *>(h->queue.p),

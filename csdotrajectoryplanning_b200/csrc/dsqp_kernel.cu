@@ -8,8 +8,6 @@
 //   isFeasible / updateCorridor     sqp/dsqp_solver.cc:292-420, 818-872
 //   generateBox & co                sqp/corridor.cc:25-324
 #include "dsqp_device.cuh"
-#include <cub/device/device_radix_sort.cuh>
-
 #include "band_solver.cuh"
 #include "dsqp_launch.h"
 #include <cstdlib>
@@ -430,10 +428,10 @@ __device__ __forceinline__ void assemble_rows(Ctx &c, const csdo_params &P) {
     const double dxf = -P.f2x * sn, dyf = P.f2x * cs, dxr = -P.r2x * sn, dyr = P.r2x * cs;
     const double exf = P.f2x * (cs + yaw0 * sn), eyf = P.f2x * (sn - yaw0 * cs);
     const double exr = P.r2x * (cs + yaw0 * sn), eyr = P.r2x * (sn - yaw0 * cs);
-    c.ros()[RO_CL0 * NT + c.t()] = c.corr()[0 * Nt + t] - exf; c.ros()[RO_CU0 * NT + c.t()] = c.corr()[1 * Nt + t] - exf;
-    c.ros()[RO_CL1 * NT + c.t()] = c.corr()[2 * Nt + t] - eyf; c.ros()[RO_CU1 * NT + c.t()] = c.corr()[3 * Nt + t] - eyf;
-    c.ros()[RO_CL2 * NT + c.t()] = c.corr()[4 * Nt + t] - exr; c.ros()[RO_CU2 * NT + c.t()] = c.corr()[5 * Nt + t] - exr;
-    c.ros()[RO_CL3 * NT + c.t()] = c.corr()[6 * Nt + t] - eyr; c.ros()[RO_CU3 * NT + c.t()] = c.corr()[7 * Nt + t] - eyr;
+    c.ros()[RO_CL0 * NT + c.t()] = __ldcg(&c.corr()[0 * Nt + t]) - exf; c.ros()[RO_CU0 * NT + c.t()] = __ldcg(&c.corr()[1 * Nt + t]) - exf;
+    c.ros()[RO_CL1 * NT + c.t()] = __ldcg(&c.corr()[2 * Nt + t]) - eyf; c.ros()[RO_CU1 * NT + c.t()] = __ldcg(&c.corr()[3 * Nt + t]) - eyf;
+    c.ros()[RO_CL2 * NT + c.t()] = __ldcg(&c.corr()[4 * Nt + t]) - exr; c.ros()[RO_CU2 * NT + c.t()] = __ldcg(&c.corr()[5 * Nt + t]) - exr;
+    c.ros()[RO_CL3 * NT + c.t()] = __ldcg(&c.corr()[6 * Nt + t]) - eyr; c.ros()[RO_CU3 * NT + c.t()] = __ldcg(&c.corr()[7 * Nt + t]) - eyr;
     for (int k = c.pstart()[t]; k < c.pstart()[t + 1]; ++k) {
       const double *pl = c.plane_abc() + (size_t)12 * k;
 #pragma unroll
@@ -900,7 +898,7 @@ __device__ __forceinline__ bool is_feasible(Ctx &c, const csdo_params &P) {
     const double Y[4] = {x0 + P.f2x * cs, y0 + P.f2x * sn, x0 + P.r2x * cs, y0 + P.r2x * sn};
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const double lo = c.corr()[(2 * q) * Nt + t], hi = c.corr()[(2 * q + 1) * Nt + t];
+      const double lo = __ldcg(&c.corr()[(2 * q) * Nt + t]), hi = __ldcg(&c.corr()[(2 * q + 1) * Nt + t]);
       if (!(lo <= Y[q])) mx[0] = fmax(mx[0], lo - Y[q]);
       if (!(Y[q] <= hi)) mx[0] = fmax(mx[0], Y[q] - hi);
     }
@@ -926,7 +924,7 @@ __device__ __forceinline__ bool is_feasible(Ctx &c, const csdo_params &P) {
 // Register budget follows the block size (one thread per time step): horizons <= 128 run with up to
 // 255 registers (2 CTAs/SM), <= 256 with 255 (1 CTA/SM), longer ones with 128.
 __device__ __forceinline__ void refine_body(const DevBatch &B, const DevOut &O, const csdo_params &P,
-                                            const Layout &LY, double *scratch, int *queue, const PassState &ST) {
+                                            const Layout &LY, double *scratch, int *queue, const QueueState &ST) {
   extern __shared__ double smem[];
   __shared__ int s_agent;
   __shared__ int s_flag;
@@ -973,13 +971,26 @@ __device__ __forceinline__ void refine_body(const DevBatch &B, const DevOut &O, 
   if (threadIdx.x == 0) cs.solver_warp = s_flag % ((blockDim.x + 31) >> 5);
   __syncthreads();
   for (;;) {
-    if (threadIdx.x == 0) s_agent = atomicAdd(queue, 1);
+    if (threadIdx.x == 0) {
+      int a_next = -1;
+      const int idx = atomicAdd(queue + kQHead, 1);
+      if (idx < ST.cap) {
+        volatile int *slot = ST.items + idx;
+        volatile int *remaining = queue + kQRemaining;
+        long long spins = 0;
+        while ((a_next = *slot) < 0) {  // the slot is filled by the CTA that re-enqueues an agent
+          if (*remaining <= 0) break;    // every SQP loop is finished: nothing will be appended any more
+          __nanosleep(200);
+          if (++spins > 50000000LL) { atomicExch(queue + kQError, 1); break; }  // safety net, never expected
+        }
+      }
+      s_agent = a_next;
+    }
     __syncthreads();
-    const int qi = s_agent;
+    const int a = s_agent;
     __syncthreads();
-    if (qi >= B.n_agents) break;
-    const int a = ST.order ? ST.order[qi] : qi;
-    if (ST.pass > 0 && ST.done[a]) continue;  // (uniform: every thread reads the same flag)
+    if (a < 0) break;
+    __threadfence();  // the agent's state was published by another CTA before its queue slot was written
     // instance of this agent: last i with inst_agent_ptr[i] <= a
     int lo = 0, hi = B.n_inst;
     while (hi - lo > 1) {
@@ -1012,11 +1023,11 @@ __device__ __forceinline__ void refine_body(const DevBatch &B, const DevOut &O, 
     }
     // solution0 and the frozen trust centre (dsqp_solver.cc:56-63); cfg (utils.cc:115-120).  Later passes
     // continue from the iterate the previous pass left in the trajectory output.
-    const bool first_pass = ST.pass == 0;
+    const bool first_pass = __ldcg(&O.sqp_iters[a]) == 0;  // (zeroed before the launch)
     if (c.active()) {
 #pragma unroll
       for (int k = 0; k < 6; ++k) {
-        double v = first_pass ? c.guess()[k * Nt + c.t()] : traj[k * Nt + c.t()];
+        double v = first_pass ? c.guess()[k * Nt + c.t()] : __ldcg(&traj[k * Nt + c.t()]);
         if (k >= 4 && !c.has_next()) v = 0.0;
         c.cur()[k * NT + c.t()] = v;
         c.sol()[k * NT + c.t()] = v;
@@ -1042,14 +1053,12 @@ __device__ __forceinline__ void refine_body(const DevBatch &B, const DevOut &O, 
       __syncthreads();
     }
 
-    // `while (delta > th && iter_count < max_iter)` (dsqp_solver.cc:99-253): the first iteration in
-    // pass 0, the remaining ones in pass 1 (see PassState)
+    // `while (delta > th && iter_count < max_iter)` (dsqp_solver.cc:99-253): one iteration per visit
+    // (see QueueState)
     const double th = P.delta_solution_threshold;
-    const bool run_to_end = ST.pass > 0;
-    int iter_count = first_pass ? 0 : O.sqp_iters[a];
-    int status = first_pass ? 1 : O.status[a];
-    int admm = first_pass ? 0 : O.admm_iters[a], nfac = first_pass ? 0 : O.n_factor[a];
-    int last_admm = 0;
+    int iter_count = first_pass ? 0 : __ldcg(&O.sqp_iters[a]);
+    int status = first_pass ? 1 : __ldcg(&O.status[a]);
+    int admm = first_pass ? 0 : __ldcg(&O.admm_iters[a]), nfac = first_pass ? 0 : __ldcg(&O.n_factor[a]);
     bool finished = true;
     __syncthreads();
     PH_ADD(0);
@@ -1058,7 +1067,7 @@ __device__ __forceinline__ void refine_body(const DevBatch &B, const DevOut &O, 
       PH_ADD(1);
       const QpOut q = solve_qp(c, P);
       PH_RESET();
-      status = q.status; admm += q.iters; nfac += q.n_factor; last_admm = q.iters;
+      status = q.status; admm += q.iters; nfac += q.n_factor;
       double s[1] = {0.0};
       if (c.active()) {
         const int nv = nvar(c);
@@ -1082,7 +1091,7 @@ __device__ __forceinline__ void refine_body(const DevBatch &B, const DevOut &O, 
         PH_ADD(0);
       }
       finished = !(delta > th && iter_count < P.max_iter);
-      if (finished || !run_to_end) break;
+      break;  // one SQP iteration per visit
     }
     // extractSingleSolutionVec2OptRes + per-agent records
     double ob[1] = {0.0};
@@ -1102,8 +1111,19 @@ __device__ __forceinline__ void refine_body(const DevBatch &B, const DevOut &O, 
     if (threadIdx.x == 0) {
       O.status[a] = status; O.sqp_iters[a] = iter_count; O.n_qp[a] = iter_count;
       O.admm_iters[a] = admm; O.n_factor[a] = nfac; O.objective[a] = ob[0];
-      ST.done[a] = finished ? 1 : 0;
-      ST.last_admm[a] = last_admm * Nt;  // sort key of the next pass: what the last QP cost
+    }
+    // publish the agent's state, then either retire it or append it to the queue for its next iteration
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (finished) {
+        atomicSub(queue + kQRemaining, 1);
+      } else {
+        const int slot = atomicAdd(queue + kQTail, 1);
+        if (slot < ST.cap) *(volatile int *)(ST.items + slot) = a;
+        else atomicExch(queue + kQError, 1);
+      }
     }
     __syncthreads();
     PH_ADD(7);
@@ -1119,12 +1139,12 @@ __device__ __forceinline__ void refine_body(const DevBatch &B, const DevOut &O, 
 template <int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
 dsqp_refine_kernel(const DevBatch B, const DevOut O, const csdo_params P, const Layout LY, double *scratch,
-                   int *queue, const PassState ST) {
+                   int *queue, const QueueState ST) {
   refine_body(B, O, P, LY, scratch, queue, ST);
 }
 
 using RefineKernel = void (*)(const DevBatch, const DevOut, const csdo_params, const Layout, double *, int *,
-                              const PassState);
+                              const QueueState);
 // lean: the variant compiled for one more resident CTA per SM.  Registers are allocated per SM
 // sub-partition (16384 each): 9 or 10 resident warps put 3 on one sub-partition, i.e. <= 168 per thread.
 static RefineKernel pick_kernel(int block, bool lean) {
@@ -1221,46 +1241,21 @@ Layout make_layout(int NT, int KMAX, int tier, int KS) {
   return l;
 }
 
-// sort keys of a pass: unfinished agents by descending cost of their last QP, finished ones last
-__global__ void pass_keys_kernel(int n, const int *done, const int *last_admm, unsigned *keys, int *vals) {
+// queue and per-agent counters before the launch
+__global__ void queue_init_kernel(int n, const int *order, int *items, int cap, int *ctrl, int *sqp_iters) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  keys[i] = done[i] ? 0xffffffffu : 0x7fffffffu - (unsigned)last_admm[i];
-  vals[i] = i;
+  if (i < cap) items[i] = i < n ? (order ? order[i] : i) : -1;
+  if (i < n) sqp_iters[i] = 0;
+  if (i == 0) { ctrl[kQHead] = 0; ctrl[kQTail] = n; ctrl[kQRemaining] = n; ctrl[kQError] = 0; }
 }
 
-namespace {
-struct PassBuf {  // carved out of one device allocation
-  int *done, *last_admm, *vals_in, *vals_out;
-  unsigned *keys_in, *keys_out;
-  void *cub_tmp;
-  size_t cub_bytes;
-};
-size_t cub_sort_bytes(int n) {
-  size_t bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const unsigned *)nullptr, (unsigned *)nullptr, (const int *)nullptr,
-                                  (int *)nullptr, n);
-  return bytes;
-}
-PassBuf carve_pass_buf(void *base, int n) {
-  PassBuf pb;
-  const size_t A = ((size_t)n + 63) & ~(size_t)63;
-  int *p = static_cast<int *>(base);
-  pb.done = p; pb.last_admm = p + A; pb.vals_in = p + 2 * A; pb.vals_out = p + 3 * A;
-  pb.keys_in = reinterpret_cast<unsigned *>(p + 4 * A); pb.keys_out = reinterpret_cast<unsigned *>(p + 5 * A);
-  pb.cub_tmp = p + 6 * A;
-  pb.cub_bytes = cub_sort_bytes(n);
-  return pb;
-}
-}  // namespace
-
-size_t refine_pass_bytes(int n_agents) {
-  const size_t A = ((size_t)n_agents + 63) & ~(size_t)63;
-  return 6 * A * sizeof(int) + cub_sort_bytes(n_agents) + 256;
+size_t refine_queue_bytes(int n_agents, const csdo_params &P) {
+  const size_t visits = (size_t)(P.max_iter > 1 ? P.max_iter : 1);
+  return ((size_t)n_agents * visits + 64) * sizeof(int);
 }
 
 cudaError_t launch_refine(const DevBatch &B, const DevOut &O, const csdo_params &P, const Layout &LY,
-                          double *scratch, int *queue, void *pass_buf, int grid, int block, bool lean,
+                          double *scratch, int *queue, void *queue_items, int grid, int block, bool lean,
                           cudaStream_t stream, int *n_launches) {
   const int smem = LY.smem_doubles * 8;
   RefineKernel kern = pick_kernel(block, lean);
@@ -1269,30 +1264,14 @@ cudaError_t launch_refine(const DevBatch &B, const DevOut &O, const csdo_params 
   if (const char *co = getenv("CSDO_CARVEOUT"))  // developer knob: shared-memory carve-out in percent
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(co));
   const int fb = 256, n = B.n_agents;
-  int launches = 0;
+  QueueState qs{static_cast<int *>(queue_items), (int)(refine_queue_bytes(n, P) / sizeof(int))};
+  e = cudaMemsetAsync(queue, 0, 2048, stream);
+  if (e != cudaSuccess) return e;
   fill_int_kernel<<<(B.n_inst + fb - 1) / fb, fb, 0, stream>>>(O.inst_static_legal, B.n_inst, 1);
-  ++launches;
-  const PassBuf pb = carve_pass_buf(pass_buf, n);
-  const int passes = P.max_iter > 1 ? 2 : 1;
-  for (int pass = 0; pass < passes; ++pass) {
-    PassState st{pass, pb.done, pb.last_admm, B.agent_order};
-    if (pass > 0) {
-      pass_keys_kernel<<<(n + fb - 1) / fb, fb, 0, stream>>>(n, pb.done, pb.last_admm, pb.keys_in, pb.vals_in);
-      size_t bytes = pb.cub_bytes;
-      e = cub::DeviceRadixSort::SortPairs(pb.cub_tmp, bytes, pb.keys_in, pb.keys_out, pb.vals_in, pb.vals_out, n, 0, 32,
-                                          stream);
-      if (e != cudaSuccess) return e;
-      st.order = pb.vals_out;
-      launches += 2;  // (+ the sort's own kernels)
-    }
-    e = cudaMemsetAsync(queue, 0, 2048, stream);
-    if (e != cudaSuccess) return e;
-    kern<<<grid, block, smem, stream>>>(B, O, P, LY, scratch, queue, st);
-    ++launches;
-  }
+  queue_init_kernel<<<(qs.cap + fb - 1) / fb, fb, 0, stream>>>(n, B.agent_order, qs.items, qs.cap, queue, O.sqp_iters);
+  kern<<<grid, block, smem, stream>>>(B, O, P, LY, scratch, queue, qs);
   aggregate_status_kernel<<<(B.n_inst + fb - 1) / fb, fb, 0, stream>>>(B, O);
-  ++launches;
-  if (n_launches) *n_launches = launches;
+  if (n_launches) *n_launches = 4;
   return cudaGetLastError();
 }
 

@@ -31,17 +31,18 @@ struct DevOut {  // device pointers, same meaning as csdo_result
   int *inst_status, *inst_static_legal;
 };
 
-// Two passes over the agents.  Pass 0 runs the FIRST SQP iteration of every agent; pass 1 runs the
-// remaining iterations to completion with the work queue sorted by what the first QP cost (ADMM
-// iterations x horizon): the agents whose QPs run into the ADMM iteration limit (a few percent of the
-// agents, ~40 % of the work) are then started first and spread over the CTAs instead of landing at the
-// end of a single pass.  Measured on the bench workload: -10 % launch time; results are unchanged (the
-// state between the passes is the trajectory / corridor / counter output arrays, all FP64 or int).
-struct PassState {
-  int pass;          // 0: first SQP iteration from the initial guess; 1: continue to the end
-  int *done;         // [n_agents] SQP loop finished
-  int *last_admm;    // [n_agents] cost of the agent's last QP (ADMM iterations x horizon)
-  const int *order;  // processing order of this pass (may be null)
+// Work queue of the refine kernel (one persistent launch).  An agent is handed out for ONE SQP
+// iteration at a time and, unless its SQP loop is finished, appended to the queue again (round-robin
+// time slicing): the agents whose QPs run into the ADMM iteration limit (a few percent of the agents,
+// ~40 % of the work, up to 10 QPs x 400 iterations) then advance together with everything else instead
+// of occupying single CTAs at the end of the launch.  The state between two visits of an agent is its
+// trajectory / corridor / counter output (FP64 / int), read back around the (non-coherent) L1.
+//   ctrl[kQHead] next queue slot to hand out, ctrl[kQTail] next free slot, ctrl[kQRemaining] agents
+//   whose SQP loop is not finished, ctrl[kQError] set if a waiting CTA gave up (never expected)
+constexpr int kQHead = 0, kQTail = 20, kQRemaining = 21, kQError = 22;
+struct QueueState {
+  int *items;  // [cap] agent ids, -1 = not written yet
+  int cap;     // n_agents x max(1, max_iter) + slack
 };
 
 // Shared-memory / scratch placement for one launch (offsets in doubles).
@@ -57,10 +58,10 @@ int refine_occupancy(int block, int smem_bytes, bool lean);
 int refine_kernel_regs(int block, bool lean);
 void read_debug_counters(unsigned long long *out16);
 
-// pass_buf: 2 n_agents ints (done, last_admm) + sort buffers, see refine_pass_bytes()
-size_t refine_pass_bytes(int n_agents);
+// queue_items: refine_queue_bytes() of device memory
+size_t refine_queue_bytes(int n_agents, const csdo_params &P);
 cudaError_t launch_refine(const DevBatch &B, const DevOut &O, const csdo_params &P, const Layout &LY,
-                          double *scratch, int *queue, void *pass_buf, int grid, int block, bool lean,
+                          double *scratch, int *queue, void *queue_items, int grid, int block, bool lean,
                           cudaStream_t stream, int *n_launches);
 cudaError_t launch_corridors(const DevBatch &B, const csdo_params &P, int double_centres, double *corridors,
                              int *box_status, int *inst_static_legal, cudaStream_t stream);

@@ -114,12 +114,12 @@ typedef struct csdo_batch {
   const int32_t *plane_ptr;      /* [n_agents+1] */
   const int32_t *plane_t;        /* [sum K] */
   const double *plane_abc;       /* [sum K][12] */
-  const int32_t *agent_order;    /* [n_agents] optional processing order of the
-                                    first SQP iteration (a permutation, longest
-                                    first balances the GPU best); NULL = the
-                                    library decides.  The remaining iterations
-                                    run in a second launch ordered by the cost
-                                    of each agent's first QP. */
+  const int32_t *agent_order;    /* [n_agents] optional initial order of the
+                                    work queue (a permutation, longest first
+                                    balances the GPU best); NULL = the library
+                                    decides.  An agent is handed out for one SQP
+                                    iteration at a time and re-enqueued until
+                                    its loop ends. */
 } csdo_batch;
 
 typedef struct csdo_result {

@@ -42,6 +42,6 @@ else:
   json.dump({"dram_bytes_per_launch": tr, "source": f"profiles/{tag}_refine_full_summary.txt (ncu --set full, bench workload: 600 instances / 9000 agents)"},
           open("profiles/traffic.json", "w"))
 open(f"profiles/{tag}_refine_full_summary.txt", "w").write(
-    "# ncu --set full --clock-control none -k regex:dsqp_refine -s 1 -c 1 python bench.py --steps 1 --warmup 0 --no-cpu-baseline\n# (the second of the two dsqp_refine_kernel launches of a step: the cost-sorted run-to-completion pass)\n"
+    "# ncu --set full --clock-control none -k regex:dsqp_refine -c 1 python bench.py --steps 1 --warmup 0 --no-cpu-baseline\n"
     + "\n".join(f"{k} = {summ[k][0]} {summ[k][1]}" for k in want if k in summ) + f"\ndram_bytes_per_launch = {tr:.0f}\n")
 print(open(f"profiles/{tag}_refine_full_summary.txt").read())
