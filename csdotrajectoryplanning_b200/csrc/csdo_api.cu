@@ -315,6 +315,11 @@ int csdo_refine(csdo_handle *h, const csdo_batch *in, csdo_result *out) {
   if ((rc = download(h, out->inst_status, O.inst_status, I))) return rc;
   if ((rc = download(h, out->inst_static_legal, O.inst_static_legal, I))) return rc;
   if (set_err(h, "refine", cudaStreamSynchronize(h->stream))) return CSDO_ERR_CUDA;
+  {  // the work queue's safety net (a CTA gave up waiting for a queue slot): never expected
+    int qerr = 0;
+    cudaMemcpy(&qerr, static_cast<int *>(h->queue.p) + kQError, sizeof(int), cudaMemcpyDeviceToHost);
+    if (qerr) { h->err = "refine: work queue stalled"; return CSDO_ERR_CUDA; }
+  }
   if (getenv("CSDO_PROFILE")) {   // developer aid (needs a -DCSDO_DEV_TIMERS build): per-phase cycles, summed over CTAs
     unsigned long long ph[8];
     cudaMemcpy(ph, static_cast<char *>(h->queue.p) + 8, sizeof(ph), cudaMemcpyDeviceToHost);
