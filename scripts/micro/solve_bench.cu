@@ -1,4 +1,5 @@
 // Developer microbenchmark: the whole band_solve_warp (as compiled for the library) on one CTA / all SMs.
+// (the factor storage holds synthetic values: timing only; compile with -DCSDO_DEV_TIMERS for the parts)
 #include <cstdio>
 #include <cuda_runtime.h>
 #include "band_solver.cuh"
@@ -8,10 +9,13 @@ __global__ void __launch_bounds__(96, 2) k(long long *cyc, double *sink, int Nt,
   BandMem bm;
   bm.L6 = sm; bm.dinv = sm + 36 * NT + kSkewPad; 
   double *rhs = bm.dinv + 6 * NT, *tmp = rhs + 6 * NT;
-  bm.Sinv = tmp + 6 * NT; bm.sv = bm.Sinv + kMaxNs * kMaxNs; bm.G = tmp;
+  bm.Sinv = tmp + 6 * NT; bm.sv = bm.Sinv + kL2Doubles; bm.G = tmp;
+  __shared__ int tab[kMaxP];
+  if (threadIdx.x == 0) fill_skew_table(Nt, tab);
+  bm.tab = tab;
   for (int i = threadIdx.x; i < 36 * NT + kSkewPad; i += blockDim.x) bm.L6[i] = 0.01 * ((i * 7) % 13) / 13.0;
   for (int i = threadIdx.x; i < 6 * NT; i += blockDim.x) { bm.dinv[i] = 1.0; rhs[i] = 1.0 + i * 1e-3; tmp[i] = 0; }
-  for (int i = threadIdx.x; i < kMaxNs * kMaxNs + 3 * kMaxNs; i += blockDim.x) bm.Sinv[i] = 1e-3;
+  for (int i = threadIdx.x; i < kL2Doubles + 3 * kMaxNs; i += blockDim.x) bm.Sinv[i] = 1e-3;
   __syncthreads();
   long long t0 = clock64();
   for (int r = 0; r < reps; ++r) {
