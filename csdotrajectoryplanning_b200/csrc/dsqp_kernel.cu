@@ -1091,7 +1091,7 @@ __device__ __forceinline__ void refine_body(const DevBatch &B, const DevOut &O, 
         PH_ADD(0);
       }
       finished = !(delta > th && iter_count < P.max_iter);
-      break;  // one SQP iteration per visit
+      if (finished || iter_count < kMaxVisits - 1) break;  // one SQP iteration per visit (see kMaxVisits)
     }
     // extractSingleSolutionVec2OptRes + per-agent records
     double ob[1] = {0.0};
@@ -1250,7 +1250,7 @@ __global__ void queue_init_kernel(int n, const int *order, int *items, int cap, 
 }
 
 size_t refine_queue_bytes(int n_agents, const csdo_params &P) {
-  const size_t visits = (size_t)(P.max_iter > 1 ? P.max_iter : 1);
+  const size_t visits = (size_t)(P.max_iter > 1 ? (P.max_iter < kMaxVisits ? P.max_iter : kMaxVisits) : 1);
   return ((size_t)n_agents * visits + 64) * sizeof(int);
 }
 

@@ -40,9 +40,12 @@ struct DevOut {  // device pointers, same meaning as csdo_result
 //   ctrl[kQHead] next queue slot to hand out, ctrl[kQTail] next free slot, ctrl[kQRemaining] agents
 //   whose SQP loop is not finished, ctrl[kQError] set if a waiting CTA gave up (never expected)
 constexpr int kQHead = 0, kQTail = 20, kQRemaining = 21, kQError = 22;
+// An agent is handed out at most kMaxVisits times: from its last visit on it runs to the end of its SQP
+// loop (bounds the queue for large QpParm::max_iter; the default max_iter = 10 never gets there).
+constexpr int kMaxVisits = 16;
 struct QueueState {
   int *items;  // [cap] agent ids, -1 = not written yet
-  int cap;     // n_agents x max(1, max_iter) + slack
+  int cap;     // n_agents x min(max(1, max_iter), kMaxVisits) + slack
 };
 
 // Shared-memory / scratch placement for one launch (offsets in doubles).
