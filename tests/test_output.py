@@ -52,3 +52,23 @@ def test_round_trip_and_status_rule(tmp_path):
     for code, want in ((1, True), (-2, True), (2, True), (3, False), (-3, False), (-7, False)):
         dump_solutions(p, tr, SolutionStatistics(solver_status=code))
         assert read_solution_status(p)[1] == want
+
+
+def test_cpp_dump_solutions_writes_the_same_file(tmp_path):
+    """include/csdo/solution_io.h (C++) and output.format_solutions (Python) produce identical text."""
+    import os, subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    subprocess.run(["make", "-C", os.path.join(here, "cpp"), "test_solution_io"], check=True, capture_output=True)
+    rng = np.random.default_rng(3)
+    tr = rng.normal(0, 20, (3, 6, 7))
+    tr[:, 3] *= 0.01; tr[:, 5] *= 0.003
+    tr[0, 1, 2] = -0.0004          # prints as -0.000 in both
+    stat = SolutionStatistics(solver_status=-2, search_status=1, rt_preprocess=0.125)
+    lines = [f"3 7 {stat.solver_status} {stat.search_status} {stat.rt_preprocess!r}"]
+    for a in range(3):
+        for t in range(7):
+            lines.append(" ".join(repr(float(tr[a, k, t])) for k in range(6)))
+    path = str(tmp_path / "cpp.yaml")
+    subprocess.run([os.path.join(here, "cpp", "test_solution_io"), path], input="\n".join(lines) + "\n", text=True,
+                   check=True)
+    assert open(path).read() == format_solutions(tr, stat)
