@@ -14,14 +14,16 @@ from .batch import CsdoBatch, CsdoLaunchInfo, CsdoResult
 from .params import CsdoParams
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libcsdo_dsqp.so")
+# CSDO_LIB (developer knob): another build of the same library, e.g. one with -DCSDO_DEV_TIMERS
+LIB_PATH = os.environ.get("CSDO_LIB") or os.path.join(_HERE, "csrc", "libcsdo_dsqp.so")
 
 CSDO_OK, CSDO_ERR_INVALID, CSDO_ERR_CUDA, CSDO_ERR_UNSUPPORTED, CSDO_ERR_NOMEM = 0, 1, 2, 3, 4
 
 EXPORTS = [
     "csdo_default_params", "csdo_version", "csdo_create", "csdo_destroy", "csdo_last_error",
     "csdo_refine", "csdo_refine_device", "csdo_last_launch", "csdo_corridors",
-    "csdo_planes_count", "csdo_planes_fill", "csdo_measure_fp64_peak",
+    "csdo_planes_count", "csdo_planes_fill", "csdo_planes_fill_partners", "csdo_planes_from_pairs",
+    "csdo_planes_count_device", "csdo_planes_fill_device", "csdo_sync", "csdo_measure_fp64_peak",
 ]
 
 _lib = None
@@ -64,6 +66,19 @@ def lib():
         L.csdo_planes_count.restype = C.c_int
         L.csdo_planes_fill.argtypes = [H, C.POINTER(CsdoBatch), C.c_void_p, C.c_void_p, C.c_void_p]
         L.csdo_planes_fill.restype = C.c_int
+        L.csdo_planes_fill_partners.argtypes = [H, C.POINTER(CsdoBatch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.csdo_planes_fill_partners.restype = C.c_int
+        L.csdo_planes_from_pairs.argtypes = [H, C.POINTER(CsdoBatch), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_void_p]
+        L.csdo_planes_from_pairs.restype = C.c_int
+        L.csdo_planes_count_device.argtypes = [H, C.POINTER(CsdoBatch), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                               C.POINTER(C.c_int64), C.c_void_p]
+        L.csdo_planes_count_device.restype = C.c_int
+        L.csdo_planes_fill_device.argtypes = [H, C.POINTER(CsdoBatch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.c_void_p]
+        L.csdo_planes_fill_device.restype = C.c_int
+        L.csdo_sync.argtypes = [H]
+        L.csdo_sync.restype = C.c_int
         L.csdo_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
         L.csdo_measure_fp64_peak.restype = C.c_int
         _lib = L

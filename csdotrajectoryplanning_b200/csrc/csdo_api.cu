@@ -22,15 +22,26 @@ struct DevBuf {
 struct csdo_handle {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t last_stream = nullptr;  // stream of the last csdo_refine_device (csdo_sync)
   csdo_params P{};
   std::string err;
   int num_sms = 0, smem_limit = 0, smem_limit_sm = 0;
-  DevBuf scratch, queue, step_cnt, pass_buf;
+  DevBuf scratch, queue, step_cnt, pass_buf, tile_sum;
   std::vector<DevBuf> stage;  // staging buffers of the host-pointer entry points
   csdo_launch_info last{};
 };
 
 namespace {
+
+// the entry points switch to the handle's device and restore the caller's current device on return
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev); else prev = -1;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 
 constexpr int PL_BYTES_PER_PLANE = 6 * 4 * 8;
 
@@ -73,11 +84,37 @@ int validate_host(csdo_handle *h, const csdo_batch *in, bool need_planes, Meta &
       if (in->agent_off[a + 1] - in->agent_off[a] != nt) { h->err = "agent_off inconsistent with inst_nt"; return CSDO_ERR_INVALID; }
   }
   m.steps = in->agent_off[in->n_agents];
+  if (in->obs_ptr[0] != 0) { h->err = "obs_ptr[0] != 0"; return CSDO_ERR_INVALID; }
+  for (int i = 0; i < in->n_inst; ++i)
+    if (in->obs_ptr[i + 1] < in->obs_ptr[i]) { h->err = "obs_ptr not monotonic"; return CSDO_ERR_INVALID; }
   m.n_obs = in->obs_ptr[in->n_inst];
+  if (m.n_obs > 0 && !in->obs) { h->err = "null obstacle array"; return CSDO_ERR_INVALID; }
   if (need_planes) {
-    for (int a = 0; a < in->n_agents; ++a) m.max_k = std::max(m.max_k, in->plane_ptr[a + 1] - in->plane_ptr[a]);
+    if (in->plane_ptr[0] != 0) { h->err = "plane_ptr[0] != 0"; return CSDO_ERR_INVALID; }
+    for (int a = 0; a < in->n_agents; ++a) {
+      if (in->plane_ptr[a + 1] < in->plane_ptr[a]) { h->err = "plane_ptr not monotonic"; return CSDO_ERR_INVALID; }
+      m.max_k = std::max(m.max_k, in->plane_ptr[a + 1] - in->plane_ptr[a]);
+    }
     m.n_planes = in->plane_ptr[in->n_agents];
     if (m.n_planes > 0 && (!in->plane_t || !in->plane_abc)) { h->err = "null plane arrays"; return CSDO_ERR_INVALID; }
+    // the kernel finds the planes of a step by binary search: sorted by t within an agent, 0 <= t < Nt
+    for (int a = 0; a < in->n_agents; ++a) {
+      const int nt = (int)(in->agent_off[a + 1] - in->agent_off[a]);
+      int prev = 0;
+      for (int k = in->plane_ptr[a]; k < in->plane_ptr[a + 1]; ++k) {
+        const int t = in->plane_t[k];
+        if (t < prev || t >= nt) { h->err = "plane_t must be sorted within an agent and lie in [0, Nt)"; return CSDO_ERR_INVALID; }
+        prev = t;
+      }
+    }
+  }
+  if (in->agent_order) {  // must be a permutation: a duplicate would let two CTAs refine one agent
+    std::vector<char> seen((size_t)in->n_agents, 0);
+    for (int a = 0; a < in->n_agents; ++a) {
+      const int v = in->agent_order[a];
+      if (v < 0 || v >= in->n_agents || seen[v]) { h->err = "agent_order is not a permutation"; return CSDO_ERR_INVALID; }
+      seen[v] = 1;
+    }
   }
   return CSDO_OK;
 }
@@ -157,20 +194,24 @@ int run_refine(csdo_handle *h, const DevBatch &B, const DevOut &O, int max_nt, i
   for (int tier = 0; tier <= 3; ++tier) {
     if (force && tier != atoi(force)) continue;
     if (!force && tier >= 2 && occ > 0) break;
-    const Layout l = make_layout(NT, KMAX, tier, 0);
+    const Layout l = make_layout(NT, KMAX, tier, 0, 0);
     if (l.smem_doubles * 8 + 1024 > h->smem_limit) continue;
-    for (int ln = 0; ln < 2; ++ln) {
+    const char *no_lean = getenv("CSDO_NO_LEAN");  // developer knob: never use the register-lean kernel variants
+    for (int ln = 0; ln < ((no_lean && atoi(no_lean)) ? 1 : 2); ++ln) {
       const int o = refine_occupancy(block, l.smem_doubles * 8, ln);
       if (o > occ) { occ = o; LY = l; lean = ln; }
     }
   }
   if (occ >= 1) {
-    // spend the shared memory that the chosen residency leaves free on the agents' plane rows
+    // spend the shared memory that the chosen residency leaves free on (1) the per-plane contribution
+    // buffer of the plane-major passes (3 doubles per plane in the ADMM loop), (2) the agents' plane rows
     // (192 B per plane): agents with K <= KS keep them on chip, the rest use global scratch
-    const int budget = h->smem_limit_sm / occ - 1024 - LY.smem_doubles * 8;
-    int KS = std::min(KMAX, std::max(0, budget / (PL_BYTES_PER_PLANE)));
+    int budget = (h->smem_limit_sm / occ - 1024 - LY.smem_doubles * 8) / 8;  // doubles
+    budget = std::max(0, budget - 8);
+    const int PC = std::min(3 * KMAX, budget) & ~1;
+    int KS = std::min(KMAX, std::max(0, (budget - PC) / (PL_BYTES_PER_PLANE / 8)));
     KS &= ~1;
-    Layout l = make_layout(NT, KMAX, LY.tier, KS);
+    Layout l = make_layout(NT, KMAX, LY.tier, KS, PC);
     if (refine_occupancy(block, l.smem_doubles * 8, lean) >= occ) LY = l;
   }
   if (occ < 1) { h->err = "horizon does not fit the kernel's shared-memory layout"; return CSDO_ERR_UNSUPPORTED; }
@@ -229,7 +270,7 @@ int csdo_create(const csdo_params *params, int device, csdo_handle **out) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return CSDO_ERR_CUDA;
   if (prop.major != 10) return CSDO_ERR_CUDA;  // sm_100a code only
-  if (cudaSetDevice(device) != cudaSuccess) return CSDO_ERR_CUDA;
+  DeviceGuard guard(device);
   csdo_handle *h = new csdo_handle();
   h->device = device;
   if (params) h->P = *params; else csdo_default_params(&h->P);
@@ -244,13 +285,14 @@ int csdo_create(const csdo_params *params, int device, csdo_handle **out) {
 
 void csdo_destroy(csdo_handle *h) {
   if (!h) return;
-  cudaSetDevice(h->device);
+  DeviceGuard guard(h->device);
   cudaStreamSynchronize(h->stream);
   for (auto &b : h->stage) if (b.p) cudaFree(b.p);
   if (h->scratch.p) cudaFree(h->scratch.p);
   if (h->queue.p) cudaFree(h->queue.p);
   if (h->step_cnt.p) cudaFree(h->step_cnt.p);
   if (h->pass_buf.p) cudaFree(h->pass_buf.p);
+  if (h->tile_sum.p) cudaFree(h->tile_sum.p);
   cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -266,17 +308,40 @@ int csdo_last_launch(const csdo_handle *h, csdo_launch_info *info) {
 int csdo_refine_device(csdo_handle *h, const csdo_batch *in, csdo_result *out, int max_nt, int max_planes,
                        void *cuda_stream) {
   if (!h || !in || !out) return CSDO_ERR_INVALID;
-  cudaSetDevice(h->device);
+  if (!out->traj || !out->corridors || !out->status || !out->sqp_iters || !out->n_qp || !out->admm_iters ||
+      !out->n_factor || !out->objective || !out->inst_status || !out->inst_static_legal) {
+    h->err = "csdo_refine_device: every csdo_result array is required"; return CSDO_ERR_INVALID;
+  }
+  if (in->n_agents > 0 && (!in->inst_agent_ptr || !in->inst_nt || !in->inst_dims || !in->obs_ptr || !in->agent_off ||
+                           !in->guess || !in->plane_ptr)) {
+    h->err = "null array in batch"; return CSDO_ERR_INVALID;
+  }
+  DeviceGuard guard(h->device);
   DevBatch B = as_dev(in);
   DevOut O{out->traj, out->corridors, out->status, out->sqp_iters, out->n_qp, out->admm_iters,
            out->n_factor, out->objective, out->inst_status, out->inst_static_legal};
   cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->stream;
+  h->last_stream = s;
   return run_refine(h, B, O, max_nt, max_planes, s);
+}
+
+int csdo_sync(csdo_handle *h) {
+  if (!h) return CSDO_ERR_INVALID;
+  DeviceGuard guard(h->device);
+  cudaStream_t s = h->last_stream ? h->last_stream : h->stream;
+  if (set_err(h, "csdo_sync", cudaStreamSynchronize(s))) return CSDO_ERR_CUDA;
+  if (!h->queue.p) return CSDO_OK;
+  int qerr = 0;
+  if (set_err(h, "csdo_sync", cudaMemcpy(&qerr, static_cast<int *>(h->queue.p) + kQError, sizeof(int), cudaMemcpyDeviceToHost)))
+    return CSDO_ERR_CUDA;
+  if (qerr == 2) { h->err = "refine: an agent has more planes than max_planes"; return CSDO_ERR_INVALID; }
+  if (qerr) { h->err = "refine: work queue stalled"; return CSDO_ERR_CUDA; }
+  return CSDO_OK;
 }
 
 int csdo_refine(csdo_handle *h, const csdo_batch *in, csdo_result *out) {
   if (!h || !in || !out) return CSDO_ERR_INVALID;
-  cudaSetDevice(h->device);
+  DeviceGuard guard(h->device);
   Meta m;
   int rc = validate_host(h, in, true, m);
   if (rc) return rc;
@@ -314,12 +379,8 @@ int csdo_refine(csdo_handle *h, const csdo_batch *in, csdo_result *out) {
   if ((rc = download(h, out->objective, O.objective, A))) return rc;
   if ((rc = download(h, out->inst_status, O.inst_status, I))) return rc;
   if ((rc = download(h, out->inst_static_legal, O.inst_static_legal, I))) return rc;
-  if (set_err(h, "refine", cudaStreamSynchronize(h->stream))) return CSDO_ERR_CUDA;
-  {  // the work queue's safety net (a CTA gave up waiting for a queue slot): never expected
-    int qerr = 0;
-    cudaMemcpy(&qerr, static_cast<int *>(h->queue.p) + kQError, sizeof(int), cudaMemcpyDeviceToHost);
-    if (qerr) { h->err = "refine: work queue stalled"; return CSDO_ERR_CUDA; }
-  }
+  h->last_stream = h->stream;
+  if ((rc = csdo_sync(h))) return rc;  // also reports the work queue's error flag
   if (getenv("CSDO_PROFILE")) {   // developer aid (needs a -DCSDO_DEV_TIMERS build): per-phase cycles, summed over CTAs
     unsigned long long ph[8];
     cudaMemcpy(ph, static_cast<char *>(h->queue.p) + 8, sizeof(ph), cudaMemcpyDeviceToHost);
@@ -328,12 +389,12 @@ int csdo_refine(csdo_handle *h, const csdo_batch *in, csdo_result *out) {
     for (int k = 0; k < 8; ++k) tot += (double)ph[k];
     for (int k = 0; k < 8; ++k)
       fprintf(stderr, "[csdo profile] %-9s %6.2f%%  %.3e cycles\n", names[k], 100.0 * ph[k] / tot, (double)ph[k]);
-    unsigned long long dbg[16];
+    unsigned long long dbg[32];
     csdo::read_debug_counters(dbg);
-    fprintf(stderr, "[csdo profile] solve parts: S1 %.3e  S2 %.3e  Sinv %.3e  S3 %.3e\n", (double)dbg[0], (double)dbg[1], (double)dbg[2], (double)dbg[3]);
-    fprintf(stderr, "[csdo profile] solve entry %.3e  caller-side call time %.3e\n", (double)dbg[11], (double)dbg[12]);
-    fprintf(stderr, "[csdo profile] factor parts: F1 %.3e  F2 %.3e  F3 %.3e (scatter %.3e  groups %.3e  R %.3e  Rinv %.3e)\n",
-            (double)dbg[4], (double)dbg[5], (double)dbg[6], (double)dbg[7], (double)dbg[8], (double)dbg[9], (double)dbg[10]);
+    static const char *dn[12] = {"S1 sweeps", "S1 barrier", "S2+barrier", "BCR levels", "S4 sweeps", "S4 scatter+barrier",
+                                 "-", "-", "rows fixed", "rows planes", "rows barrier", "rows finish"};
+    for (int k = 0; k < 12; ++k)
+      if (dbg[k]) fprintf(stderr, "[csdo profile] solve/rows part %-20s %.3e cycles\n", dn[k], (double)dbg[k]);
   }
   return CSDO_OK;
 }
@@ -341,7 +402,7 @@ int csdo_refine(csdo_handle *h, const csdo_batch *in, csdo_result *out) {
 int csdo_corridors(csdo_handle *h, const csdo_batch *in, int double_centres, double *corridors,
                    int32_t *box_status, int32_t *inst_static_legal) {
   if (!h || !in || !corridors) return CSDO_ERR_INVALID;
-  cudaSetDevice(h->device);
+  DeviceGuard guard(h->device);
   Meta m;
   int rc = validate_host(h, in, false, m);
   if (rc) return rc;
@@ -362,43 +423,75 @@ int csdo_corridors(csdo_handle *h, const csdo_batch *in, int double_centres, dou
   return CSDO_OK;
 }
 
+int csdo_planes_count_device(csdo_handle *h, const csdo_batch *in, int64_t total_steps, int32_t *step_off,
+                             int32_t *plane_ptr, int32_t *inst_inter_legal, int64_t *total_planes, void *cuda_stream) {
+  if (!h || !in || !step_off || !plane_ptr || !inst_inter_legal) return CSDO_ERR_INVALID;
+  DeviceGuard guard(h->device);
+  cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->stream;
+  if (total_planes) *total_planes = 0;
+  if (in->n_agents == 0) return CSDO_OK;
+  const DevBatch B = as_dev(in);
+  const int n_tiles = (int)((total_steps + 2047) / 2048);
+  int rc = ensure(h, h->tile_sum, ((size_t)n_tiles + 2) * sizeof(int));
+  if (rc) return rc;
+  if (set_err(h, "launch_planes_count", launch_planes_count(B, h->P, step_off, inst_inter_legal, s))) return CSDO_ERR_CUDA;
+  if (set_err(h, "launch_plane_offsets",
+              launch_plane_offsets(B, total_steps, step_off, static_cast<int *>(h->tile_sum.p), plane_ptr, s)))
+    return CSDO_ERR_CUDA;
+  h->last.launches = 6;
+  if (total_planes) {
+    int tot = 0;
+    if (set_err(h, "planes total", cudaMemcpyAsync(&tot, step_off + total_steps, sizeof(int), cudaMemcpyDeviceToHost, s)) ||
+        set_err(h, "planes_count", cudaStreamSynchronize(s)))
+      return CSDO_ERR_CUDA;
+    if (tot < 0) { h->err = "plane count overflows int32"; return CSDO_ERR_UNSUPPORTED; }
+    *total_planes = tot;
+  }
+  return CSDO_OK;
+}
+
+int csdo_planes_fill_device(csdo_handle *h, const csdo_batch *in, const int32_t *step_off, int32_t *plane_t,
+                            double *plane_abc, int32_t *plane_partner, void *cuda_stream) {
+  if (!h || !in || !step_off) return CSDO_ERR_INVALID;
+  DeviceGuard guard(h->device);
+  cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->stream;
+  if (in->n_agents == 0) return CSDO_OK;
+  if (!plane_t || !plane_abc) return CSDO_ERR_INVALID;
+  if (set_err(h, "launch_planes_fill", launch_planes_fill(as_dev(in), h->P, step_off, plane_t, plane_abc, plane_partner, s)))
+    return CSDO_ERR_CUDA;
+  h->last.launches = 1;
+  return CSDO_OK;
+}
+
 int csdo_planes_count(csdo_handle *h, const csdo_batch *in, int32_t *plane_ptr, int32_t *inst_inter_legal) {
   if (!h || !in || !plane_ptr) return CSDO_ERR_INVALID;
-  cudaSetDevice(h->device);
+  DeviceGuard guard(h->device);
   Meta m;
   int rc = validate_host(h, in, false, m);
   if (rc) return rc;
   plane_ptr[0] = 0;
+  if (inst_inter_legal) for (int i = 0; i < in->n_inst; ++i) inst_inter_legal[i] = 1;
   if (in->n_agents == 0) return CSDO_OK;
   DevBatch B;
   if ((rc = upload_batch(h, in, m, false, B))) return rc;
-  if ((rc = ensure(h, h->step_cnt, ((size_t)m.steps + in->n_inst + 1) * sizeof(int)))) return rc;
-  int *d_cnt = static_cast<int *>(h->step_cnt.p), *d_legal = d_cnt + m.steps;
-  if (set_err(h, "launch_planes_count", launch_planes_count(B, h->P, d_cnt, d_legal, h->stream))) return CSDO_ERR_CUDA;
-  std::vector<int> cnt((size_t)m.steps);
-  if ((rc = download(h, cnt.data(), d_cnt, (size_t)m.steps))) return rc;
+  if ((rc = ensure(h, h->step_cnt, ((size_t)m.steps + 1 + in->n_inst + in->n_agents + 1) * sizeof(int)))) return rc;
+  int *d_off = static_cast<int *>(h->step_cnt.p), *d_legal = d_off + m.steps + 1, *d_ptr = d_legal + in->n_inst;
+  csdo_batch dv = *in;
+  dv.inst_agent_ptr = B.inst_agent_ptr; dv.inst_nt = B.inst_nt; dv.inst_dims = B.inst_dims; dv.obs_ptr = B.obs_ptr;
+  dv.obs = B.obs; dv.agent_off = B.agent_off; dv.guess = B.guess; dv.plane_ptr = nullptr; dv.plane_t = nullptr;
+  dv.plane_abc = nullptr; dv.agent_order = nullptr;
+  int64_t total = 0;
+  if ((rc = csdo_planes_count_device(h, &dv, m.steps, d_off, d_ptr, d_legal, &total, h->stream))) return rc;
+  if ((rc = download(h, plane_ptr, d_ptr, (size_t)in->n_agents + 1))) return rc;
   if ((rc = download(h, inst_inter_legal, d_legal, (size_t)in->n_inst))) return rc;
   if (set_err(h, "planes_count", cudaStreamSynchronize(h->stream))) return CSDO_ERR_CUDA;
-  // exclusive scan over (agent, step): plane index of the first plane of each step
-  int64_t run = 0;
-  for (int a = 0; a < in->n_agents; ++a) {
-    plane_ptr[a] = (int)run;
-    for (int64_t s = in->agent_off[a]; s < in->agent_off[a + 1]; ++s) { const int c = cnt[s]; cnt[s] = (int)run; run += c; }
-  }
-  plane_ptr[in->n_agents] = (int)run;
-  if (run > INT32_MAX) { h->err = "plane count overflows int32"; return CSDO_ERR_UNSUPPORTED; }
-  if (set_err(h, "cudaMemcpy step offsets",
-              cudaMemcpyAsync(d_cnt, cnt.data(), (size_t)m.steps * sizeof(int), cudaMemcpyHostToDevice, h->stream)))
-    return CSDO_ERR_CUDA;
-  if (set_err(h, "planes_count", cudaStreamSynchronize(h->stream))) return CSDO_ERR_CUDA;
-  h->last.launches = 2;
   return CSDO_OK;
 }
 
-int csdo_planes_fill(csdo_handle *h, const csdo_batch *in, const int32_t *plane_ptr, int32_t *plane_t,
-                     double *plane_abc) {
+int csdo_planes_fill_partners(csdo_handle *h, const csdo_batch *in, const int32_t *plane_ptr, int32_t *plane_t,
+                              double *plane_abc, int32_t *plane_partner) {
   if (!h || !in || !plane_ptr) return CSDO_ERR_INVALID;
-  cudaSetDevice(h->device);
+  DeviceGuard guard(h->device);
   Meta m;
   int rc = validate_host(h, in, false, m);
   if (rc) return rc;
@@ -406,19 +499,72 @@ int csdo_planes_fill(csdo_handle *h, const csdo_batch *in, const int32_t *plane_
   const size_t total = (size_t)plane_ptr[in->n_agents];
   if (total == 0) return CSDO_OK;
   if (!plane_t || !plane_abc) return CSDO_ERR_INVALID;
-  if (h->step_cnt.cap < (size_t)m.steps * sizeof(int)) { h->err = "csdo_planes_count must precede csdo_planes_fill"; return CSDO_ERR_INVALID; }
+  if (h->step_cnt.cap < ((size_t)m.steps + 1) * sizeof(int)) { h->err = "csdo_planes_count must precede csdo_planes_fill"; return CSDO_ERR_INVALID; }
   DevBatch B;
   if ((rc = upload_batch(h, in, m, false, B))) return rc;
-  int *d_t; double *d_abc;
+  int *d_t, *d_partner = nullptr; double *d_abc;
   if ((rc = devalloc(h, 8, total, &d_t))) return rc;
   if ((rc = devalloc(h, 9, 12 * total, &d_abc))) return rc;
+  if (plane_partner && (rc = devalloc(h, 15, total, &d_partner))) return rc;
   if (set_err(h, "launch_planes_fill",
-              launch_planes_fill(B, h->P, static_cast<int *>(h->step_cnt.p), d_t, d_abc, h->stream)))
+              launch_planes_fill(B, h->P, static_cast<int *>(h->step_cnt.p), d_t, d_abc, d_partner, h->stream)))
     return CSDO_ERR_CUDA;
   h->last.launches = 1;
   if ((rc = download(h, plane_t, d_t, total))) return rc;
   if ((rc = download(h, plane_abc, d_abc, 12 * total))) return rc;
+  if (plane_partner && (rc = download(h, plane_partner, d_partner, total))) return rc;
   if (set_err(h, "planes_fill", cudaStreamSynchronize(h->stream))) return CSDO_ERR_CUDA;
+  return CSDO_OK;
+}
+
+int csdo_planes_fill(csdo_handle *h, const csdo_batch *in, const int32_t *plane_ptr, int32_t *plane_t,
+                     double *plane_abc) {
+  return csdo_planes_fill_partners(h, in, plane_ptr, plane_t, plane_abc, nullptr);
+}
+
+int csdo_planes_from_pairs(csdo_handle *h, const csdo_batch *in, int64_t n_pairs, const int32_t *pairs,
+                           int32_t *plane_ptr, int32_t *plane_t, double *plane_abc) {
+  if (!h || !in || !plane_ptr || n_pairs < 0 || (n_pairs > 0 && !pairs)) return CSDO_ERR_INVALID;
+  DeviceGuard guard(h->device);
+  Meta m;
+  int rc = validate_host(h, in, false, m);
+  if (rc) return rc;
+  const int A = in->n_agents;
+  for (int a = 0; a <= A; ++a) plane_ptr[a] = 0;
+  if (A == 0 || n_pairs == 0) return CSDO_OK;
+  if (2 * n_pairs > INT32_MAX) { h->err = "plane count overflows int32"; return CSDO_ERR_UNSUPPORTED; }
+  if (!plane_t || !plane_abc) return CSDO_ERR_INVALID;
+  // every pair pushes one plane to agent i and one to agent j, in list order (inter_agent_cons.cc:136-137)
+  for (int64_t p = 0; p < n_pairs; ++p) {
+    const int t = pairs[3 * p], i = pairs[3 * p + 1], j = pairs[3 * p + 2];
+    if (i < 0 || j < 0 || i >= A || j >= A || i == j || t < 0 || t >= in->agent_off[i + 1] - in->agent_off[i] ||
+        in->agent_off[j + 1] - in->agent_off[j] != in->agent_off[i + 1] - in->agent_off[i]) {
+      h->err = "invalid neighbour pair"; return CSDO_ERR_INVALID;
+    }
+    plane_ptr[i + 1]++; plane_ptr[j + 1]++;
+  }
+  for (int a = 0; a < A; ++a) plane_ptr[a + 1] += plane_ptr[a];
+  std::vector<int> cursor(plane_ptr, plane_ptr + A), pos((size_t)2 * n_pairs);
+  for (int64_t p = 0; p < n_pairs; ++p) {
+    pos[2 * p] = cursor[pairs[3 * p + 1]]++;
+    pos[2 * p + 1] = cursor[pairs[3 * p + 2]]++;
+  }
+  DevBatch B;
+  if ((rc = upload_batch(h, in, m, false, B))) return rc;
+  const int *d_pairs, *d_pos;
+  if ((rc = upload(h, 16, pairs, (size_t)3 * n_pairs, &d_pairs))) return rc;
+  if ((rc = upload(h, 17, pos.data(), pos.size(), &d_pos))) return rc;
+  int *d_t; double *d_abc;
+  const size_t total = (size_t)2 * n_pairs;
+  if ((rc = devalloc(h, 8, total, &d_t))) return rc;
+  if ((rc = devalloc(h, 9, 12 * total, &d_abc))) return rc;
+  if (set_err(h, "launch_planes_from_pairs",
+              launch_planes_from_pairs(B, h->P, n_pairs, d_pairs, d_pos, d_t, d_abc, h->stream)))
+    return CSDO_ERR_CUDA;
+  h->last.launches = 1;
+  if ((rc = download(h, plane_t, d_t, total))) return rc;
+  if ((rc = download(h, plane_abc, d_abc, 12 * total))) return rc;
+  if (set_err(h, "planes_from_pairs", cudaStreamSynchronize(h->stream))) return CSDO_ERR_CUDA;
   return CSDO_OK;
 }
 

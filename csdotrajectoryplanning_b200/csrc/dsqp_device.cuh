@@ -8,7 +8,7 @@
 // rows, x,y,yaw,steer of step t+1, so thread t regenerates its rows from a few
 // per-step coefficients (visit_rows below).  In time-major order the reduced
 // KKT matrix P + sigma I + A' diag(rho) A is symmetric positive definite with
-// half-bandwidth 6; its LDL' factor lives in shared memory.
+// half-bandwidth 6; its factor lives in shared memory (pbcr_solver.cuh).
 #pragma once
 
 #include <cuda_runtime.h>
@@ -18,11 +18,25 @@
 #include "csdo_dsqp.h"
 
 namespace csdo {
+// developer counters: cycle timers, compiled in with -DCSDO_DEV_TIMERS (make DEV=-DCSDO_DEV_TIMERS) and
+// printed by csdo_refine when CSDO_PROFILE is set.  Thread 0 of every CTA accumulates clock64 deltas.
+__device__ unsigned long long g_dbg[32];
+}
+#ifdef CSDO_DEV_TIMERS
+#define DBG_INIT() long long dbg_t_ = clock64()
+#define DBG_ACC(i) do { if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&csdo::g_dbg[i], (unsigned long long)(t_ - dbg_t_)); dbg_t_ = t_; } } while (0)
+#else
+#define DBG_INIT() do {} while (0)
+#define DBG_ACC(i) do {} while (0)
+#endif
+
+#include "pbcr_solver.cuh"
+
+namespace csdo {
 
 constexpr double kRhoMin = 1e-6, kRhoMax = 1e6, kRhoEqOverIneq = 1e3, kRhoTol = 1e-4;
 constexpr double kMinScaling = 1e-4, kMaxScaling = 1e4, kOsqpInfty = 1e30;
 constexpr int kBand = 6;        // half bandwidth of the reduced KKT in time-major order
-constexpr int kLw = kBand + 1;  // stored entries per row: 1/d_i and 6 sub-diagonals
 
 // read-only per-step planes (stride NT)
 enum Ro : int {
@@ -34,25 +48,11 @@ enum Pl : int { PL_A = 0, PL_B, PL_G, PL_U, PL_E, PL_W, PL_COUNT };
 // local unknown indices inside visit_rows: own step 0..5, next step x,y,yaw,steer 6..9
 enum Var : int { VX = 0, VY, VP, VS, VV, VW, NX, NY, NP, NS };
 
-// band solver geometry (band_solver.cuh)
-constexpr int kMaxP = 16;                 // horizon partitions (lanes of the solver warp)
-constexpr int kMaxNs = 6 * (kMaxP - 1);   // separator unknowns
-constexpr int kL2Tinv = 4 * 18 * 18, kL2R = 18 * 18, kL2B = 6 * 36;  // level-2 inverses and couplings
-constexpr int kL2Doubles = kL2Tinv + kL2R + kL2B;
-constexpr int kSkewPad = 256;  // extra doubles at the end of the L6 area (<= 16 partitions x 14 doubles)
-
-struct BandMem {
-  double *L6, *dinv;  // [(6t+k)*6 + d-1], [6t+k]; generic pointers (shared or global)
-  double *Sinv;       // level-2 inverses of the separator system, kL2Doubles (shared)
-  double *sv;         // 3 * kMaxNs scratch: g, x_sep, z / pivot rows (shared)
-  double *G;          // factor-time scratch: per partition GCC[21] GBB[21] GBC[36] = 78 * kMaxP doubles (shared)
-  const int *tab;     // bank-skew table of the partitions (shared context)
-};
 
 // CTA-uniform context of the agent being refined.  It lives in SHARED memory (written by thread 0
 // between barriers): keeping two dozen pointers per thread in registers starved the row passes.
 struct CtxShared {
-  int Nt, NT, K, KP, No, KS, solver_warp;
+  int Nt, NT, K, KP, No, KS;
   bool l_shared, rows_glob;
   // shared-memory vectors, SoA with stride NT: v[k*NT + t]
   double *x, *xt, *rhs, *D, *carry, *red;
@@ -61,12 +61,15 @@ struct CtxShared {
   double *cfgs;  // 6 start/goal pins
   double *Es;    // Ruiz row scaling of the fixed rows, 16 planes (read-only during the ADMM loop)
   double *ws;    // ADMM row state w = z_hat + y/rho of the fixed rows, 16 planes
-  BandMem bm;    // band factor storage (band_solver.cuh)
-  int skew_tab[kMaxP];
+  PbcrMem pm;    // reduced-KKT factor storage (pbcr_solver.cuh)
+  csdo_params P; // copy of the parameters for the out-of-line (cold) phases
+  void *fn_solve; // band solve entry point (indirect call, see dsqp_kernel.cu)
   // per-CTA global scratch
   double *cur, *sol, *dy;
   double *pl;    // plane rows of this agent: shared memory when they fit (K <= KS), else global scratch
   double *pl_smem, *pl_glob;
+  double *pc_smem, *pc_glob;  // per-plane contributions of a plane-major pass (visit_planes)
+  int pc_cap;                 // doubles of pc_smem
   // batch views of this agent
   const double *guess;      // 6 planes, stride Nt
   const double *plane_abc;  // [K][12]
@@ -74,7 +77,6 @@ struct CtxShared {
   const double *obs;        // [No][3]
   double *corr;             // 8 planes, stride Nt (output array doubles as the live corridor)
   double dimx, dimy;
-  void *fn_solve, *fn_factor;  // band solve / factor entry points (indirect calls, see dsqp_kernel.cu)
 };
 
 // Per-thread handle: the shared context plus the few values that change inside a QP.
@@ -86,16 +88,17 @@ struct Ctx {
 #endif
 #define CSDO_GET(type, name) __device__ __forceinline__ type name() const { return s->name; }
   CSDO_GET(int, Nt) CSDO_GET(int, NT) CSDO_GET(int, K) CSDO_GET(int, KP) CSDO_GET(int, No) CSDO_GET(int, KS)
-  CSDO_GET(int, solver_warp) CSDO_GET(bool, l_shared) CSDO_GET(bool, rows_glob)
+  CSDO_GET(bool, l_shared) CSDO_GET(bool, rows_glob)
   CSDO_GET(double *, x) CSDO_GET(double *, xt) CSDO_GET(double *, rhs) CSDO_GET(double *, D)
   CSDO_GET(double *, carry) CSDO_GET(double *, red) CSDO_GET(int *, pstart) CSDO_GET(double *, ros)
   CSDO_GET(double *, cfgs) CSDO_GET(double *, Es) CSDO_GET(double *, ws)
   CSDO_GET(double *, cur) CSDO_GET(double *, sol) CSDO_GET(double *, dy) CSDO_GET(double *, pl)
-  CSDO_GET(double *, pl_smem) CSDO_GET(double *, pl_glob)
+  CSDO_GET(double *, pl_smem) CSDO_GET(double *, pl_glob) CSDO_GET(double *, pc_smem) CSDO_GET(double *, pc_glob)
+  CSDO_GET(int, pc_cap)
   CSDO_GET(const double *, guess) CSDO_GET(const double *, plane_abc) CSDO_GET(const int *, plane_t)
   CSDO_GET(const double *, obs) CSDO_GET(double *, corr) CSDO_GET(double, dimx) CSDO_GET(double, dimy)
 #undef CSDO_GET
-  __device__ __forceinline__ const BandMem &bm() const { return s->bm; }
+  __device__ __forceinline__ const PbcrMem &pm() const { return s->pm; }
   // one thread per time step
   __device__ __forceinline__ int tid() const { return threadIdx.x; }
   __device__ __forceinline__ int nthr() const { return blockDim.x; }
@@ -152,30 +155,54 @@ __device__ __forceinline__ void block_reduce(double (&v)[N], double *red) {
 // of the 13 every-step rows are read into registers up front and written back once at the end: with
 // the values behind shared-memory references the compiler had to keep every load behind the previous
 // row's store (possible aliasing) and the pass ran one row at a time.
-template <class F>
-__device__ __forceinline__ void visit_rows(Ctx &c, const csdo_params &P, F &f) {
-  const int t = c.t();
-  __builtin_assume(__isShared(c.pstart()));  // (row data, E and w may live in global scratch: generic loads)
-  const int NTs = c.NT();
+struct RowRegs {
   double ro[RO_COUNT], E[13], w[13];
-  const bool rows_glob = c.rows_glob();
-  {
-    const double *ro_ = c.ros() + t, *Ep = c.Es() + t, *wp = c.ws() + t;
-    if (rows_glob) {  // global scratch (plain loads: the read-only part is reused from L1 across passes)
+};
+
+__device__ __forceinline__ void rows_load(const Ctx &c, RowRegs &R) {
+  const int t = c.t(), NTs = c.NT();
+  const double *ro_ = c.ros() + t, *Ep = c.Es() + t, *wp = c.ws() + t;
+  if (c.rows_glob()) {  // global scratch (plain loads: the read-only part is reused from L1 across passes)
 #pragma unroll
-      for (int i = 0; i < RO_COUNT; ++i) ro[i] = ro_[i * NTs];
+    for (int i = 0; i < RO_COUNT; ++i) R.ro[i] = ro_[i * NTs];
 #pragma unroll
-      for (int i = 0; i < 13; ++i) { E[i] = Ep[i * NTs]; w[i] = wp[i * NTs]; }
-    } else {
-      __builtin_assume(__isShared(ro_)); __builtin_assume(__isShared(Ep)); __builtin_assume(__isShared(wp));
+    for (int i = 0; i < 13; ++i) { R.E[i] = Ep[i * NTs]; R.w[i] = wp[i * NTs]; }
+  } else {
+    __builtin_assume(__isShared(ro_)); __builtin_assume(__isShared(Ep)); __builtin_assume(__isShared(wp));
 #pragma unroll
-      for (int i = 0; i < RO_COUNT; ++i) ro[i] = ro_[i * NTs];
+    for (int i = 0; i < RO_COUNT; ++i) R.ro[i] = ro_[i * NTs];
 #pragma unroll
-      for (int i = 0; i < 13; ++i) { E[i] = Ep[i * NTs]; w[i] = wp[i * NTs]; }
+    for (int i = 0; i < 13; ++i) { R.E[i] = Ep[i * NTs]; R.w[i] = wp[i * NTs]; }
+  }
+}
+
+template <bool WRITE_W, bool WRITE_E>
+__device__ __forceinline__ void rows_store(const Ctx &c, const RowRegs &R) {
+  const int t = c.t(), NTs = c.NT();
+  double *Ep = c.Es() + t, *wp = c.ws() + t;
+  if (c.rows_glob()) {
+#pragma unroll
+    for (int i = 0; i < 13; ++i) {
+      if (WRITE_W) wp[i * NTs] = R.w[i];
+      if (WRITE_E) Ep[i * NTs] = R.E[i];
+    }
+  } else {
+    __builtin_assume(__isShared(Ep)); __builtin_assume(__isShared(wp));
+#pragma unroll
+    for (int i = 0; i < 13; ++i) {
+      if (WRITE_W) wp[i * NTs] = R.w[i];
+      if (WRITE_E) Ep[i * NTs] = R.E[i];
     }
   }
-  const int k0 = c.pstart()[t], k1 = c.pstart()[t + 1];
-#define RO(i) ro[i]
+}
+
+// the 13 every-step rows (+ 3 start/goal rows) of this thread's step, from registers
+template <class F>
+__device__ __forceinline__ void rows_apply(Ctx &c, const csdo_params &P, F &f, RowRegs &R) {
+  const int t = c.t(), NTs = c.NT();
+  double (&w)[13] = R.w;
+  double (&E)[13] = R.E;
+#define RO(i) R.ro[i]
   const double sn = RO(RO_SN), cs = RO(RO_CS);
   if (c.has_next()) {
     // calcKineConstraint :646-744, lb = ub = -C
@@ -207,32 +234,40 @@ __device__ __forceinline__ void visit_rows(Ctx &c, const csdo_params &P, F &f) {
   }
   f.template row<1>(12, VS, 1.0, 0, 0.0, 0, 0.0, 0, 0.0, -P.steer_max, P.steer_max, w[12], E[12]);
 #undef RO
-  {
-    double *Ep = c.Es() + t, *wp = c.ws() + t;
-    if (rows_glob) {
-#pragma unroll
-      for (int i = 0; i < 13; ++i) {
-        if (F::kWriteW) wp[i * NTs] = w[i];
-        if (F::kWriteE) Ep[i * NTs] = E[i];
-      }
-    } else {
-      __builtin_assume(__isShared(Ep)); __builtin_assume(__isShared(wp));
-#pragma unroll
-      for (int i = 0; i < 13; ++i) {
-        if (F::kWriteW) wp[i * NTs] = w[i];
-        if (F::kWriteE) Ep[i * NTs] = E[i];
-      }
-    }
-  }
-  // calcInterVehicleConstraint :1097-1129: 4 rows per plane of this step, l = -inf.  One plane = 4 rows
-  // = 12 16-byte loads issued together, processed from registers, w and E written back together.
-  // On-chip plane rows use plain shared-memory loads (LDS); overflow rows live in global scratch (L2):
-  // there the next plane is fetched while the current one is processed.
-  if (c.pl() == c.pl_smem()) {
-    __builtin_assume(__isShared(c.pl_smem()));
-    for (int k = k0; k < k1; ++k) {
-      double2 *q2 = reinterpret_cast<double2 *>(c.pl_smem() + (size_t)PL_COUNT * 4 * k);
-      double v[4][PL_COUNT];
+}
+
+template <class F>
+__device__ __forceinline__ void visit_rows(Ctx &c, const csdo_params &P, F &f) {
+  RowRegs R;
+  rows_load(c, R);
+  rows_apply(c, P, f, R);
+  rows_store<F::kWriteW, F::kWriteE>(c, R);
+}
+
+// ---- the inter-vehicle rows (calcInterVehicleConstraint, dsqp_solver.cc:1097-1129), PLANE-MAJOR ----
+// 4 rows per plane, l = -inf.  Thread i handles planes i, i + nthr, ... of the agent (an agent has about
+// one plane per step on average but up to ~8 on a crowded step: handled by the step's own thread, the
+// passes waited for the slowest thread and paid one L2 round trip per plane, serially).  Every plane is
+// processed by a fresh copy g of the caller's functor: plane_begin loads the three unknowns the rows touch
+// (x, y, yaw of the plane's step), the 4 rows run from registers, plane_emit writes what the rows
+// contribute to the step (3 or 6 doubles) to the contribution buffer, and after a barrier the step's thread
+// folds its planes' contributions in plane order (plane_absorb): deterministic, no atomics.
+// IN selects the per-step input: the current iterate D x (xt), D x~ right after a solve (D, rhs), D itself.
+enum PlaneIn : int { IN_NONE = 0, IN_XT, IN_DXT, IN_D };
+
+template <int IN, class F>
+__device__ __forceinline__ void visit_planes(Ctx &c, const csdo_params &P, F &f) {
+  const int K = c.K();
+  if (K == 0) return;  // CTA-uniform
+  const int NT = c.NT();
+  constexpr int NOUT = F::kPlaneOut;
+  double *pc = (NOUT * K <= c.pc_cap()) ? c.pc_smem() : c.pc_glob();
+  const bool on_chip = c.pl() == c.pl_smem();
+  for (int k = c.tid(); k < K; k += c.nthr()) {
+    double2 *q2 = reinterpret_cast<double2 *>(c.pl() + (size_t)PL_COUNT * 4 * k);
+    double v[4][PL_COUNT];
+    if (on_chip) {
+      __builtin_assume(__isShared(q2));
 #pragma unroll
       for (int r = 0; r < 4; ++r)
 #pragma unroll
@@ -241,45 +276,47 @@ __device__ __forceinline__ void visit_rows(Ctx &c, const csdo_params &P, F &f) {
           v[r][2 * h] = d2.x;
           v[r][2 * h + 1] = d2.y;
         }
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-        f.template row<3>(-1, VX, v[r][PL_A], VY, v[r][PL_B], VP, v[r][PL_G], 0, 0.0, -INFINITY, v[r][PL_U],
-                          v[r][PL_W], v[r][PL_E]);
-      if (F::kWriteW || F::kWriteE) {
-#pragma unroll
-        for (int r = 0; r < 4; ++r) q2[r * (PL_COUNT / 2) + PL_E / 2] = make_double2(v[r][PL_E], v[r][PL_W]);
-      }
-    }
-  } else if (k0 < k1) {
-    double2 nx[4 * (PL_COUNT / 2)];
-    {
-      const double2 *q2 = reinterpret_cast<const double2 *>(c.pl_glob() + (size_t)PL_COUNT * 4 * k0);
-#pragma unroll
-      for (int i = 0; i < 4 * (PL_COUNT / 2); ++i) nx[i] = q2[i];
-    }
-    for (int k = k0; k < k1; ++k) {
-      double2 *q2 = reinterpret_cast<double2 *>(c.pl_glob() + (size_t)PL_COUNT * 4 * k);
-      double v[4][PL_COUNT];
+    } else {
 #pragma unroll
       for (int r = 0; r < 4; ++r)
 #pragma unroll
         for (int h = 0; h < PL_COUNT / 2; ++h) {
-          v[r][2 * h] = nx[r * (PL_COUNT / 2) + h].x;
-          v[r][2 * h + 1] = nx[r * (PL_COUNT / 2) + h].y;
+          const double2 d2 = q2[r * (PL_COUNT / 2) + h];
+          v[r][2 * h] = d2.x;
+          v[r][2 * h + 1] = d2.y;
         }
-      if (k + 1 < k1) {
-        const double2 *qn = q2 + 4 * (PL_COUNT / 2);
-#pragma unroll
-        for (int i = 0; i < 4 * (PL_COUNT / 2); ++i) nx[i] = qn[i];
+    }
+    F g = f;
+    double in3[3] = {0.0, 0.0, 0.0};
+    if (IN != IN_NONE) {
+      const int t = c.plane_t()[k];
+      if (IN == IN_XT) {
+        in3[0] = c.xt()[VX * NT + t]; in3[1] = c.xt()[VY * NT + t]; in3[2] = c.xt()[VP * NT + t];
+      } else if (IN == IN_DXT) {
+        in3[0] = c.D()[VX * NT + t] * c.rhs()[VX * NT + t];
+        in3[1] = c.D()[VY * NT + t] * c.rhs()[VY * NT + t];
+        in3[2] = c.D()[VP * NT + t] * c.rhs()[VP * NT + t];
+      } else {
+        in3[0] = c.D()[VX * NT + t]; in3[1] = c.D()[VY * NT + t]; in3[2] = c.D()[VP * NT + t];
       }
+    }
+    g.plane_begin(in3);
 #pragma unroll
-      for (int r = 0; r < 4; ++r)
-        f.template row<3>(-1, VX, v[r][PL_A], VY, v[r][PL_B], VP, v[r][PL_G], 0, 0.0, -INFINITY, v[r][PL_U],
-                          v[r][PL_W], v[r][PL_E]);
-      if (F::kWriteW || F::kWriteE) {
+    for (int r = 0; r < 4; ++r)
+      g.template row<3>(-1, VX, v[r][PL_A], VY, v[r][PL_B], VP, v[r][PL_G], 0, 0.0, -INFINITY, v[r][PL_U],
+                        v[r][PL_W], v[r][PL_E]);
+    if (F::kWriteW || F::kWriteE) {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) q2[r * (PL_COUNT / 2) + PL_E / 2] = make_double2(v[r][PL_E], v[r][PL_W]);
-      }
+      for (int r = 0; r < 4; ++r) q2[r * (PL_COUNT / 2) + PL_E / 2] = make_double2(v[r][PL_E], v[r][PL_W]);
+    }
+    if (NOUT > 0) g.plane_emit(pc + (size_t)NOUT * k);
+    f.plane_merge(g);
+  }
+  if (NOUT > 0) {
+    __syncthreads();
+    if (c.active()) {
+      const int k0 = c.pstart()[c.t()], k1 = c.pstart()[c.t() + 1];
+      for (int k = k0; k < k1; ++k) f.plane_absorb(pc + (size_t)NOUT * k);
     }
   }
 }

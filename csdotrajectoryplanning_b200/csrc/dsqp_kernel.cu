@@ -8,21 +8,10 @@
 //   isFeasible / updateCorridor     sqp/dsqp_solver.cc:292-420, 818-872
 //   generateBox & co                sqp/corridor.cc:25-324
 #include "dsqp_device.cuh"
-#include "band_solver.cuh"
 #include "dsqp_launch.h"
 #include <cstdlib>
 
 namespace csdo {
-
-// The band factor/solve are entered through function pointers read from device memory: an indirect
-// call follows the full ABI, so the callee may use the whole register file (a direct call to the
-// kernel-local clone leaves it only the ~77 registers that are not live in the caller, which makes the
-// sweeps 1.6-3x slower); the solver warp saves/restores its live registers around the call instead.
-using BandSolveFn = void (*)(const BandMem, double *, double *, int, int);
-using BandFactorFn = void (*)(const BandMem, int);
-__device__ BandSolveFn g_band_solve[2] = {band_solve_warp<false>, band_solve_warp<true>};
-__device__ BandFactorFn g_band_factor[2] = {band_factor_warp<false>, band_factor_warp<true>};
-
 
 // ===================================================================
 // corridor boxes (sqp/corridor.cc) -- adds/compares only, bit-exact
@@ -255,6 +244,14 @@ __device__ __forceinline__ void row_scatter(double (&acc)[10], double g, int i0,
 template <int MODE>
 struct StepF {
   static constexpr bool kWriteW = true, kWriteE = false;
+  static constexpr int kPlaneOut = 3;  // visit_planes: A' (rho z - y) on x, y, yaw of the plane's step
+  __device__ __forceinline__ void plane_begin(const double (&in)[3]) {
+    xv[VX] = in[0]; xv[VY] = in[1]; xv[VP] = in[2];
+    acc[VX] = 0.0; acc[VY] = 0.0; acc[VP] = 0.0;
+  }
+  __device__ __forceinline__ void plane_emit(double *o) const { o[0] = acc[VX]; o[1] = acc[VY]; o[2] = acc[VP]; }
+  __device__ __forceinline__ void plane_absorb(const double *o) { acc[VX] += o[0]; acc[VY] += o[1]; acc[VP] += o[2]; }
+  __device__ __forceinline__ void plane_merge(const StepF &) {}
   double xv[10];
   double acc[10];
   double alpha, rho, rho_old;
@@ -302,6 +299,20 @@ enum Norm : int {
 };
 struct CheckF {
   static constexpr bool kWriteW = false, kWriteE = false;
+  static constexpr int kPlaneOut = 3;  // A'y of the plane rows (delta_y is only kept for agents without planes)
+  __device__ __forceinline__ void plane_begin(const double (&in)[3]) {
+    xv[VX] = in[0]; xv[VY] = in[1]; xv[VP] = in[2];
+    acc[VX] = 0.0; acc[VY] = 0.0; acc[VP] = 0.0;
+#pragma unroll
+    for (int k = 0; k < N_COUNT; ++k) nrm[k] = 0.0;
+    ineq_lhs = 0.0;
+  }
+  __device__ __forceinline__ void plane_emit(double *o) const { o[0] = acc[VX]; o[1] = acc[VY]; o[2] = acc[VP]; }
+  __device__ __forceinline__ void plane_absorb(const double *o) { acc[VX] += o[0]; acc[VY] += o[1]; acc[VP] += o[2]; }
+  __device__ __forceinline__ void plane_merge(const CheckF &g) {  // row norms: maxima, any order
+#pragma unroll
+    for (int k = 0; k < N_COUNT; ++k) nrm[k] = fmax(nrm[k], g.nrm[k]);
+  }
   double xv[10];
   double acc[10];   // A'y (raw-space accumulation)
   double accd[10];  // A'delta_y
@@ -340,6 +351,16 @@ struct CheckF {
 // one Ruiz pass over the rows (OSQP scale_data): row norms -> E, column maxima
 struct ScaleF {
   static constexpr bool kWriteW = false, kWriteE = true;
+  static constexpr int kPlaneOut = 3;  // column maxima on x, y, yaw of the plane's step
+  __device__ __forceinline__ void plane_begin(const double (&in)[3]) {
+    dv[VX] = in[0]; dv[VY] = in[1]; dv[VP] = in[2];
+    cmax[VX] = 0.0; cmax[VY] = 0.0; cmax[VP] = 0.0;
+  }
+  __device__ __forceinline__ void plane_emit(double *o) const { o[0] = cmax[VX]; o[1] = cmax[VY]; o[2] = cmax[VP]; }
+  __device__ __forceinline__ void plane_absorb(const double *o) {
+    cmax[VX] = fmax(cmax[VX], o[0]); cmax[VY] = fmax(cmax[VY], o[1]); cmax[VP] = fmax(cmax[VP], o[2]);
+  }
+  __device__ __forceinline__ void plane_merge(const ScaleF &) {}
   double dv[10];    // current D of the touched unknowns
   double cmax[10];  // max_i E_i |a_ij| per touched unknown (without D_j)
   template <int NC, bool EQ = false>
@@ -359,6 +380,11 @@ struct ScaleF {
 // reset E to 1 before scaling
 struct ResetF {
   static constexpr bool kWriteW = true, kWriteE = true;
+  static constexpr int kPlaneOut = 0;
+  __device__ __forceinline__ void plane_begin(const double (&)[3]) {}
+  __device__ __forceinline__ void plane_emit(double *) const {}
+  __device__ __forceinline__ void plane_absorb(const double *) {}
+  __device__ __forceinline__ void plane_merge(const ResetF &) {}
   template <int NC, bool EQ = false>
   __device__ __forceinline__ void row(int, int, double, int, double, int, double, int, double, double, double,
                                       double &w, double &E) {
@@ -371,6 +397,17 @@ struct ResetF {
 // to the next step and the next step's diagonal contributions.
 struct HasmF {
   static constexpr bool kWriteW = false, kWriteE = false;
+  static constexpr int kPlaneOut = 6;  // lower triangle of the (x, y, yaw) block
+  __device__ __forceinline__ void plane_begin(const double (&)[3]) {
+    q[VX][VX] = 0.0; q[VY][VX] = 0.0; q[VY][VY] = 0.0; q[VP][VX] = 0.0; q[VP][VY] = 0.0; q[VP][VP] = 0.0;
+  }
+  __device__ __forceinline__ void plane_emit(double *o) const {
+    o[0] = q[VX][VX]; o[1] = q[VY][VX]; o[2] = q[VY][VY]; o[3] = q[VP][VX]; o[4] = q[VP][VY]; o[5] = q[VP][VP];
+  }
+  __device__ __forceinline__ void plane_absorb(const double *o) {
+    q[VX][VX] += o[0]; q[VY][VX] += o[1]; q[VY][VY] += o[2]; q[VP][VX] += o[3]; q[VP][VY] += o[4]; q[VP][VP] += o[5];
+  }
+  __device__ __forceinline__ void plane_merge(const HasmF &) {}
   double q[6][6];   // q[i][j], j <= i
   double cr[4][6];  // rows = next-step x,y,yaw,steer; cols = own unknowns
   double nd[4];
@@ -453,22 +490,26 @@ __device__ __forceinline__ void assemble_rows(Ctx &c, const csdo_params &P) {
 // OSQP scale_data, `scaling` Ruiz passes; leaves D, E, c
 __device__ __forceinline__ void ruiz_scale(Ctx &c, const csdo_params &P) {
   const int NT = c.NT(), t = c.t(), Nt = c.Nt();
+  ResetF rf;
   if (c.active()) {
-    ResetF rf;
     visit_rows(c, P, rf);
 #pragma unroll
     for (int k = 0; k < 6; ++k) c.D()[k * NT + t] = 1.0;
   }
+  visit_planes<IN_NONE>(c, P, rf);
   c.c = 1.0;
   __syncthreads();
   for (int pass = 0; pass < P.scaling; ++pass) {
     double dt_new[6];
+    ScaleF sf;
     if (c.active()) {
-      ScaleF sf;
       load_xv(c, c.D(), sf.dv);
 #pragma unroll
       for (int k = 0; k < 10; ++k) sf.cmax[k] = 0.0;
       visit_rows(c, P, sf);
+    }
+    visit_planes<IN_D>(c, P, sf);
+    if (c.active()) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) c.carry()[k * NT + t] = sf.cmax[6 + k];
 #pragma unroll
@@ -529,6 +570,7 @@ __device__ __forceinline__ void ruiz_scale(Ctx &c, const csdo_params &P) {
 __device__ __forceinline__ void form_and_factor(Ctx &c, const csdo_params &P) {
   const int NT = c.NT(), t = c.t(), Nt = c.Nt();
   HasmF hf;
+  hf.rho = c.rho;
   if (c.active()) {
 #pragma unroll
     for (int i = 0; i < 6; ++i)
@@ -540,23 +582,22 @@ __device__ __forceinline__ void form_and_factor(Ctx &c, const csdo_params &P) {
 #pragma unroll
       for (int j = 0; j < 6; ++j) hf.cr[i][j] = 0.0;
     }
-    hf.rho = c.rho;
     visit_rows(c, P, hf);
+  }
+  visit_planes<IN_NONE>(c, P, hf);
+  if (c.active()) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) c.carry()[k * NT + t] = hf.nd[k];
-    // clear this step's band rows; the last step's missing v, w are dummy unknowns (H_ii = 1)
-    const int sk0 = make_parts(Nt, c.s->skew_tab).skew_of_block(t);
+    // clear this step's block record; the last step's missing v, w are dummy unknowns (H_ii = 1)
+    double *B = pbcr_blk(c.pm().L, t);
 #pragma unroll
-    for (int k = 0; k < 6; ++k) {
+    for (int i = 0; i < 36; ++i) B[i] = 0.0;
 #pragma unroll
-      for (int d = 0; d < 6; ++d) c.bm().L6[sk0 + (size_t)(6 * t + k) * 6 + d] = 0.0;
-      c.bm().dinv[6 * t + k] = 1.0;
-    }
+    for (int k = 0; k < 6; ++k) B[36 + k] = 1.0;
   }
   __syncthreads();
   if (c.active()) {
     const int nv = nvar(c);
-    const Parts pt_ = make_parts(Nt, c.s->skew_tab);
     double dk[10];
     load_xv(c, c.D(), dk);
     // objective (dsqp_solver.cc:163-197): second difference on v, identity on w
@@ -564,32 +605,28 @@ __device__ __forceinline__ void form_and_factor(Ctx &c, const csdo_params &P) {
       hf.q[VV][VV] += c.c * ((t != 0 && t != Nt - 2) ? 2.0 : 1.0);
       hf.q[VW][VW] += c.c * 1.0;
     }
+    double *B = pbcr_blk(c.pm().L, t);
     for (int k = 0; k < nv; ++k) {
-      double *Lr = c.bm().L6 + pt_.skew_of_block(t) + (size_t)(6 * t + k) * 6 - 1;  // Lr[d] = H_{i,i-d}
+      double *Lr = B + 6 * k - 1;  // Lr[d] = H_{i,i-d}
       double diag = hf.q[k][k];
       if (k < 4 && t > 0) diag += c.carry()[k * NT + t - 1];
-      c.bm().dinv[6 * t + k] = dk[k] * dk[k] * diag + P.sigma;
+      B[36 + k] = dk[k] * dk[k] * diag + P.sigma;
       for (int j = 0; j < k; ++j) Lr[k - j] = dk[k] * dk[j] * hf.q[k][j];
     }
     if (c.has_next()) {
       const int nvn = (t + 1 < Nt - 1) ? 6 : 4;
+      double *Bn = pbcr_blk(c.pm().L, t + 1);
       for (int k = 0; k < 4; ++k) {  // rows x,y,yaw,steer of step t+1
-        double *Lr = c.bm().L6 + pt_.skew_of_block(t + 1) + (size_t)(6 * (t + 1) + k) * 6 - 1;
+        double *Lr = Bn + 6 * k - 1;
         for (int j = k; j < 6; ++j) Lr[6 + k - j] = dk[6 + k] * dk[j] * hf.cr[k][j];
       }
-      if (nvn == 6) {  // v_{t+1} - v_t coupling of the objective
-        double *Lr = c.bm().L6 + pt_.skew_of_block(t + 1) + (size_t)(6 * (t + 1) + VV) * 6 - 1;
-        Lr[6] = c.D()[VV * NT + t + 1] * dk[VV] * (-c.c);
-      }
+      if (nvn == 6)  // v_{t+1} - v_t coupling of the objective
+        (Bn + 6 * VV - 1)[6] = c.D()[VV * NT + t + 1] * dk[VV] * (-c.c);
     }
   }
   __syncthreads();
-  __syncwarp();
-  if ((c.tid() >> 5) == c.solver_warp()) {
-    BandFactorFn fn = reinterpret_cast<BandFactorFn>(c.s->fn_factor);
-    fn(c.bm(), Nt);
-  }
-  __syncthreads();
+  if (c.l_shared()) pbcr_factor_cta<true>(c.pm(), Nt);
+  else pbcr_factor_cta<false>(c.pm(), Nt);
 }
 
 // optional phase timing (thread 0's clock), accumulated per CTA and added to queue[2..] at exit
@@ -624,9 +661,15 @@ __device__ __forceinline__ void finish_rhs(const Ctx &c, const csdo_params &P, c
 
 // AFTER_SOLVE: x~ sits in rhs (scaled space).  The row pass then forms D x~ of this and the next step
 // itself and does the relaxed x update of its own step on the way (no separate pass, no barrier).
+// RR (optional): the step's row data / scaling / state held in registers by the caller across ADMM
+// iterations (then nothing of the fixed rows is read from or written to memory here)
 template <int MODE, bool AFTER_SOLVE = false>
-__device__ __forceinline__ void step_rows(Ctx &c, const csdo_params &P, bool store_dy, double rho_old) {
+__device__ __forceinline__ void step_rows(Ctx &c, const csdo_params &P, bool store_dy, double rho_old,
+                                          RowRegs *RR = nullptr) {
+  DBG_INIT();
   StepF<MODE> sf;
+  sf.alpha = P.alpha; sf.rho = c.rho; sf.rho_old = rho_old;
+  sf.store_dy = store_dy; sf.dy_base = c.dy() + c.t(); sf.dy_stride = c.NT();
   if (c.active()) {
     if (AFTER_SOLVE) {
       const int NT = c.NT(), t = c.t(), nv = nvar(c);
@@ -643,15 +686,21 @@ __device__ __forceinline__ void step_rows(Ctx &c, const csdo_params &P, bool sto
     }
 #pragma unroll
     for (int k = 0; k < 10; ++k) sf.acc[k] = 0.0;
-    sf.alpha = P.alpha; sf.rho = c.rho; sf.rho_old = rho_old;
-    sf.store_dy = store_dy; sf.dy_base = c.dy() + c.t(); sf.dy_stride = c.NT();
-    visit_rows(c, P, sf);
+    if (RR) rows_apply(c, P, sf, *RR);
+    else visit_rows(c, P, sf);
+  }
+  if (MODE == 2) DBG_ACC(8);    // fixed rows (thread 0's own)
+  visit_planes<MODE == 3 ? IN_NONE : (AFTER_SOLVE ? IN_DXT : IN_XT)>(c, P, sf);
+  if (MODE == 2) DBG_ACC(9);    // plane-major pass + barrier + absorb
+  if (c.active()) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) c.carry()[k * c.NT() + c.t()] = sf.acc[6 + k];
   }
   __syncthreads();  // every thread has read its neighbour's x~ before rhs is rebuilt
+  if (MODE == 2) DBG_ACC(10);   // barrier: waiting for the slowest thread of the row pass
   finish_rhs(c, P, sf.acc);
   __syncthreads();
+  if (MODE == 2) DBG_ACC(11);   // finish_rhs + barrier
 }
 
 // OSQP update_info + check_termination(approximate = false/true) on the reduced scalars
@@ -673,12 +722,15 @@ __device__ __forceinline__ void check_rows(Ctx &c, const csdo_params &P, bool wi
 #pragma unroll
   for (int k = 0; k < N_COUNT; ++k) cf.nrm[k] = 0.0;
   cf.ineq_lhs = 0.0;
+  cf.rho = c.rho; cf.with_dy = with_dy; cf.dy_base = c.dy() + c.t(); cf.dy_stride = c.NT();
   if (c.active()) {
     load_xv(c, c.xt(), cf.xv);
 #pragma unroll
     for (int k = 0; k < 10; ++k) { cf.acc[k] = 0.0; cf.accd[k] = 0.0; }
-    cf.rho = c.rho; cf.with_dy = with_dy; cf.dy_base = c.dy() + c.t(); cf.dy_stride = c.NT();
     visit_rows(c, P, cf);
+  }
+  visit_planes<IN_XT>(c, P, cf);
+  if (c.active()) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       c.carry()[k * NT + t] = cf.acc[6 + k];
@@ -747,15 +799,81 @@ __device__ int termination_status(const Ctx &c, const csdo_params &P, const Chec
   return 0;
 }
 
+// -------------------------------------------------------------------------------------------------
+// Out-of-line ("cold") entry points.  Everything that runs once per QP, once per 25 ADMM iterations or
+// once per SQP iteration is kept OUT of the ADMM loop's function body: inlined, those phases (the
+// factorization alone is 12 k SASS instructions, and it was inlined twice) set the register allocation of
+// the whole kernel, and the hot loop (band solve + row pass) ended up re-loading spilled scalars from
+// local memory at L2 latency.  The wrappers take the shared context pointer and the two per-QP scalars by
+// value (a by-reference Ctx would live in local memory) and read the parameters from the context.
+__device__ __forceinline__ Ctx make_ctx(CtxShared *s, double rho, double cc) {
+  __builtin_assume(__isShared(s));
+  Ctx c;
+  c.s = s; c.rho = rho; c.c = cc;
+#ifdef CSDO_DEV_TIMERS
+  for (int k = 0; k < 8; ++k) c.ph[k] = 0;
+#endif
+  return c;
+}
+template <int RC>
+__device__ __noinline__ double ruiz_scale_cold(CtxShared *s) {
+  Ctx c = make_ctx(s, 0.0, 1.0);
+  ruiz_scale(c, s->P);
+  return c.c;
+}
+template <int RC>
+__device__ __noinline__ void form_and_factor_cold(CtxShared *s, double rho, double cc) {
+  Ctx c = make_ctx(s, rho, cc);
+  form_and_factor(c, s->P);
+}
+template <int RC>
+__device__ __noinline__ void assemble_rows_cold(CtxShared *s) {
+  Ctx c = make_ctx(s, 0.0, 1.0);
+  assemble_rows(c, s->P);
+}
+template <int RC, int MODE, bool AFTER_SOLVE>
+__device__ __noinline__ void step_rows_cold(CtxShared *s, double rho, double cc, bool store_dy, double rho_old) {
+  Ctx c = make_ctx(s, rho, cc);
+  step_rows<MODE, AFTER_SOLVE>(c, s->P, store_dy, rho_old);
+}
+template <int RC>
+__device__ __noinline__ void check_rows_cold(CtxShared *s, double rho, double cc, bool with_dy, CheckOut *co) {
+  Ctx c = make_ctx(s, rho, cc);
+  check_rows(c, s->P, with_dy, *co);
+}
+template <int RC>
+__device__ __noinline__ int termination_status_cold(CtxShared *s, double cc, const CheckOut *co, bool approximate) {
+  Ctx c = make_ctx(s, 0.0, cc);
+  return termination_status(c, s->P, *co, approximate);
+}
+
+// the band solve as its own function: its register allocation (the sweeps want ~200 registers) is then
+// independent of what the ADMM loop keeps live
+template <int RC>
+__device__ __noinline__ void band_solve_call(CtxShared *s) {
+  __builtin_assume(__isShared(s));
+  const PbcrMem pm = s->pm;
+  if (s->l_shared) pbcr_solve_cta<true>(pm, s->rhs, s->xt, s->Nt, s->NT);
+  else pbcr_solve_cta<false>(pm, s->rhs, s->xt, s->Nt, s->NT);
+}
+
 // solveOSQP (dsqp_solver.cc:423-555): setup + warm start + ADMM; solution in c.sol()
-__device__ __forceinline__ QpOut solve_qp(Ctx &c, const csdo_params &P) {
+
+
+using BandSolveFn = void (*)(CtxShared *);
+__device__ BandSolveFn g_band_solve[3] = {band_solve_call<0>, band_solve_call<1>, band_solve_call<2>};
+
+// RC: register class of the kernel variant (0: 255, 1: 168, 2: 128 registers).  The out-of-line phases are
+// instantiated per class: a function shared by all variants would be compiled for the smallest budget.
+template <int RC>
+__device__ __forceinline__ QpOut solve_qp(Ctx &c, const csdo_params &P, const Layout &LY) {
   const int NT = c.NT(), t = c.t(), Nt = c.Nt();
   QpOut out{CSDO_QP_UNSOLVED, 0, 1};
   PH_T0();
-  ruiz_scale(c, P);
+  c.c = ruiz_scale_cold<RC>(c.s);
   PH_ADD(2);
   c.rho = fmin(fmax(P.rho, kRhoMin), kRhoMax);
-  form_and_factor(c, P);
+  form_and_factor_cold<RC>(c.s, c.rho, c.c);
   PH_ADD(3);
   // osqp_warm_start_x: x <- Dinv x0, z <- A x, y = 0
   if (c.active()) {
@@ -768,39 +886,22 @@ __device__ __forceinline__ QpOut solve_qp(Ctx &c, const csdo_params &P) {
     }
   }
   __syncthreads();
-  step_rows<0>(c, P, false, 0.0);
+  step_rows_cold<RC, 0, false>(c.s, c.rho, c.c, false, 0.0);
   const bool keep_dy = (c.K() == 0);
   CheckOut co;
   bool checked = false;
   int iter = 0;
   PH_ADD(5);
   for (iter = 1; iter <= P.osqp_max_iter; ++iter) {
-    __syncwarp();  // the solver warp must enter the solve converged (threads leave barriers individually)
-    if ((c.tid() >> 5) == c.solver_warp()) {
-      BandSolveFn fn = reinterpret_cast<BandSolveFn>(c.s->fn_solve);  // read once per CTA from global, kept in shared
-#ifdef CSDO_DEV_TIMERS
-      const long long tc0 = clock64();
-#endif
-#ifdef CSDO_INLINE_SOLVE
-      if (c.l_shared()) band_solve_body<true>(c.bm(), c.rhs(), c.xt(), Nt, NT);
-      else
-#endif
-      fn(c.bm(), c.rhs(), c.xt(), Nt, NT);
-#ifdef CSDO_DEV_TIMERS
-      if ((threadIdx.x & 31) == 0) atomicAdd(&g_dbg[12], (unsigned long long)(clock64() - tc0));
-#endif
-#ifdef CSDO_DOUBLE_SOLVE  // timing experiment: a second, discarded solve right after the first (warm instruction cache)
-      PH_ADD(4);
-      band_solve_warp<true>(c.bm(), c.xt(), c.xt(), Nt, NT);
-      PH_ADD(7);
-#endif
-    }
-    __syncthreads();
+    // entered through a function pointer read from device memory: an indirect call follows the full ABI, so
+    // the callee may use the whole register file (a direct call leaves it only the registers that are
+    // not live in the caller)
+    reinterpret_cast<BandSolveFn>(c.s->fn_solve)(c.s);
     PH_ADD(4);
     const bool can_check = P.check_termination && (iter % P.check_termination == 0);
     const bool store_dy = keep_dy && (can_check || iter == P.osqp_max_iter);
-    if (iter == 1) step_rows<1, true>(c, P, store_dy, 0.0);
-    else step_rows<2, true>(c, P, store_dy, 0.0);
+    if (iter == 1) step_rows_cold<RC, 1, true>(c.s, c.rho, c.c, store_dy, 0.0);
+    else step_rows_cold<RC, 2, true>(c.s, c.rho, c.c, store_dy, 0.0);
     PH_ADD(5);
     checked = false;
     const bool adapt = P.adaptive_rho && P.adaptive_rho_interval && (iter % P.adaptive_rho_interval == 0);
@@ -811,7 +912,7 @@ __device__ __forceinline__ QpOut solve_qp(Ctx &c, const csdo_params &P) {
 #pragma unroll
         for (int k = 0; k < 6; ++k) keep[k] = c.rhs()[k * NT + t];
       __syncthreads();
-      check_rows(c, P, keep_dy && store_dy, co);
+      check_rows_cold<RC>(c.s, c.rho, c.c, keep_dy && store_dy, &co);
       PH_ADD(6);
       if (c.active())
 #pragma unroll
@@ -819,7 +920,7 @@ __device__ __forceinline__ QpOut solve_qp(Ctx &c, const csdo_params &P) {
       __syncthreads();
       checked = can_check;
       if (can_check) {
-        const int st = termination_status(c, P, co, false);
+        const int st = termination_status_cold<RC>(c.s, c.c, &co, false);
         if (st != 0) { out.status = st; break; }
       }
       if (adapt) {
@@ -833,9 +934,10 @@ __device__ __forceinline__ QpOut solve_qp(Ctx &c, const csdo_params &P) {
           const double rho_old = c.rho;
           c.rho = rho_new;
           out.n_factor++;
-          form_and_factor(c, P);
+          form_and_factor_cold<RC>(c.s, c.rho, c.c);
           PH_ADD(3);
-          step_rows<3>(c, P, false, rho_old);
+          step_rows_cold<RC, 3, false>(c.s, c.rho, c.c, false, rho_old);
+
           PH_ADD(5);
         }
       }
@@ -850,16 +952,16 @@ __device__ __forceinline__ QpOut solve_qp(Ctx &c, const csdo_params &P) {
 #pragma unroll
         for (int k = 0; k < 6; ++k) keep[k] = c.rhs()[k * NT + t];
       __syncthreads();
-      check_rows(c, P, keep_dy, co);
+      check_rows_cold<RC>(c.s, c.rho, c.c, keep_dy, &co);
       if (c.active())
 #pragma unroll
         for (int k = 0; k < 6; ++k) c.rhs()[k * NT + t] = keep[k];
       __syncthreads();
-      const int st = termination_status(c, P, co, false);
+      const int st = termination_status_cold<RC>(c.s, c.c, &co, false);
       if (st != 0) out.status = st;
     }
     if (out.status == CSDO_QP_UNSOLVED) {
-      const int st = termination_status(c, P, co, true);
+      const int st = termination_status_cold<RC>(c.s, c.c, &co, true);
       out.status = st != 0 ? st : CSDO_QP_MAX_ITER_REACHED;
     }
   }
@@ -918,11 +1020,26 @@ __device__ __forceinline__ bool is_feasible(Ctx &c, const csdo_params &P) {
   return err_kin < 1e-2 && mx[1] < 1e-1 && mx[0] < 1e-1;
 }
 
+template <int RC>
+__device__ __noinline__ bool is_feasible_cold(CtxShared *s) {
+  Ctx c = make_ctx(s, 0.0, 1.0);
+  return is_feasible(c, s->P);
+}
+// initial corridors from the guess (float centres) or regeneration from the new iterate (double centres)
+template <int RC>
+__device__ __noinline__ int corridors_cold(CtxShared *s, bool from_solution, double *stage, int stage_doubles) {
+  Ctx c = make_ctx(s, 0.0, 1.0);
+  const int Nt = c.Nt(), NT = c.NT();
+  if (from_solution) return agent_corridors(c, s->P, c.sol(), c.sol() + NT, c.sol() + 2 * NT, stage, stage_doubles, true, nullptr);
+  return agent_corridors(c, s->P, c.guess(), c.guess() + Nt, c.guess() + 2 * Nt, stage, stage_doubles, false, nullptr);
+}
+
 // ===================================================================
 // the kernel
 // ===================================================================
 // Register budget follows the block size (one thread per time step): horizons <= 128 run with up to
 // 255 registers (2 CTAs/SM), <= 256 with 255 (1 CTA/SM), longer ones with 128.
+template <int RC>
 __device__ __forceinline__ void refine_body(const DevBatch &B, const DevOut &O, const csdo_params &P,
                                             const Layout &LY, double *scratch, int *queue, const QueueState &ST) {
   extern __shared__ double smem[];
@@ -935,6 +1052,8 @@ __device__ __forceinline__ void refine_body(const DevBatch &B, const DevOut &O, 
   double *slot = scratch + (size_t)blockIdx.x * LY.slot_doubles;
   if (threadIdx.x == 0) {
     cs.NT = LY.NT; cs.KP = 4 * LY.KMAX;
+    cs.P = P;
+    cs.fn_solve = reinterpret_cast<void *>(*(volatile BandSolveFn *)&g_band_solve[RC]);
     cs.x = smem + LY.o_x; cs.xt = smem + LY.o_xt; cs.rhs = smem + LY.o_rhs; cs.D = smem + LY.o_D;
     cs.carry = smem + LY.o_carry; cs.red = smem + LY.o_red;
     const bool rows_glob = LY.tier & 1;
@@ -944,31 +1063,20 @@ __device__ __forceinline__ void refine_body(const DevBatch &B, const DevOut &O, 
     cs.Es = rows_glob ? slot + LY.g_E : smem + LY.o_E;
     cs.ws = rows_glob ? slot + LY.g_w : smem + LY.o_w;
     cs.pstart = reinterpret_cast<int *>(smem + LY.o_pstart);
-    cs.bm.L6 = (LY.tier & 2) ? slot + LY.g_L : smem + LY.o_L;
-    cs.bm.dinv = cs.bm.L6 + 36 * NT + kSkewPad;
+    cs.pm.L = (LY.tier & 2) ? slot + LY.g_L : smem + LY.o_L;
     cs.l_shared = !(LY.tier & 2);
-    cs.bm.Sinv = smem + LY.o_sinv;
-    cs.bm.sv = cs.bm.Sinv + kL2Doubles;
-    cs.bm.tab = cs.skew_tab;
-    cs.bm.G = cs.xt;  // xt, rhs and carry are contiguous (16 NT doubles) and free while a factorization runs
+    cs.pm.S = smem + LY.o_sinv;
+    cs.pm.g = cs.carry;                    // carry, xt are free while a solve runs
+    cs.pm.y = cs.xt;
+    cs.pm.xs = cs.xt + 6 * (NT / kPM);
     cs.cur = slot + LY.g_cur; cs.sol = slot + LY.g_sol; cs.dy = slot + LY.g_dy;
     cs.pl_glob = slot + LY.g_pl; cs.pl_smem = smem + LY.o_pl; cs.KS = LY.KS;
-    cs.fn_solve = reinterpret_cast<void *>(*(volatile BandSolveFn *)&g_band_solve[cs.l_shared ? 1 : 0]);
-    cs.fn_factor = reinterpret_cast<void *>(*(volatile BandFactorFn *)&g_band_factor[cs.l_shared ? 1 : 0]);
+    cs.pc_glob = slot + LY.g_pc; cs.pc_smem = smem + LY.o_pc; cs.pc_cap = LY.PC;
   }
 
 #ifdef CSDO_DEV_TIMERS
   for (int k = 0; k < 8; ++k) c.ph[k] = 0;
 #endif
-  // The warp that runs the band factor/solve differs between the CTAs resident on one SM, so that
-  // their (single-warp, issue-bound) solves land on different SM sub-partitions (warp id % 4).
-  if (threadIdx.x == 0) {
-    unsigned smid;
-    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    s_flag = atomicAdd(queue + 32 + (smid & 255), 1);
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) cs.solver_warp = s_flag % ((blockDim.x + 31) >> 5);
   __syncthreads();
   for (;;) {
     if (threadIdx.x == 0) {
@@ -1002,7 +1110,6 @@ __device__ __forceinline__ void refine_body(const DevBatch &B, const DevOut &O, 
     const int64_t off = B.agent_off[a];
     if (threadIdx.x == 0) {
       cs.Nt = Nt;
-      fill_skew_table(Nt, cs.skew_tab);
       cs.K = B.plane_ptr[a + 1] - B.plane_ptr[a];
       cs.pl = cs.K <= cs.KS ? cs.pl_smem : cs.pl_glob;
       cs.plane_t = B.plane_t + B.plane_ptr[a];
@@ -1045,9 +1152,7 @@ __device__ __forceinline__ void refine_body(const DevBatch &B, const DevOut &O, 
     PH_T0();
     if (first_pass) {
       // calcCorridors (dsqp_solver.cc:1154) on float disc centres
-      if (agent_corridors(c, P, c.guess(), c.guess() + Nt, c.guess() + 2 * Nt, smem + LY.o_x, LY.o_carry - LY.o_x,
-                          false, nullptr))
-        s_flag = 1;
+      if (corridors_cold<RC>(c.s, false, smem + LY.o_x, LY.o_carry - LY.o_x)) s_flag = 1;
       __syncthreads();
       if (threadIdx.x == 0 && s_flag) atomicAnd(&O.inst_static_legal[inst], 0);
       __syncthreads();
@@ -1063,9 +1168,9 @@ __device__ __forceinline__ void refine_body(const DevBatch &B, const DevOut &O, 
     __syncthreads();
     PH_ADD(0);
     while (iter_count < P.max_iter) {
-      assemble_rows(c, P);
+      assemble_rows_cold<RC>(c.s);
       PH_ADD(1);
-      const QpOut q = solve_qp(c, P);
+      const QpOut q = solve_qp<RC>(c, P, LY);
       PH_RESET();
       status = q.status; admm += q.iters; nfac += q.n_factor;
       double s[1] = {0.0};
@@ -1078,15 +1183,14 @@ __device__ __forceinline__ void refine_body(const DevBatch &B, const DevOut &O, 
       block_reduce<1, false>(s, c.red());
       const double delta = s[0];
       iter_count++;
-      if (iter_count > P.max_iter / 2 && is_feasible(c, P)) { finished = true; break; }
+      if (iter_count > P.max_iter / 2 && is_feasible_cold<RC>(c.s)) { finished = true; break; }
       if (c.active())
 #pragma unroll
         for (int k = 0; k < 6; ++k) c.cur()[k * NT + c.t()] = c.sol()[k * NT + c.t()];
       __syncthreads();
       if (!P.fixed_corridor) {
         PH_ADD(7);
-        agent_corridors(c, P, c.sol(), c.sol() + NT, c.sol() + 2 * NT, smem + LY.o_x, LY.o_carry - LY.o_x, true,
-                        nullptr);
+        corridors_cold<RC>(c.s, true, smem + LY.o_x, LY.o_carry - LY.o_x);
         __syncthreads();
         PH_ADD(0);
       }
@@ -1129,7 +1233,7 @@ __device__ __forceinline__ void refine_body(const DevBatch &B, const DevOut &O, 
     PH_ADD(7);
   }
 #ifdef CSDO_DEV_TIMERS
-  if (threadIdx.x == 32 * c.solver_warp()) {  // lane 0 of the solver warp: it works in every phase
+  if (threadIdx.x == 0) {
     unsigned long long *prof = reinterpret_cast<unsigned long long *>(queue + 2);
     for (int k = 0; k < 8; ++k) atomicAdd(prof + k, (unsigned long long)c.ph[k]);
   }
@@ -1140,7 +1244,7 @@ template <int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
 dsqp_refine_kernel(const DevBatch B, const DevOut O, const csdo_params P, const Layout LY, double *scratch,
                    int *queue, const QueueState ST) {
-  refine_body(B, O, P, LY, scratch, queue, ST);
+  refine_body<(MAXT == 512) ? 2 : (((MAXT == 96 && MINB == 3) || (MAXT == 160 && MINB == 2)) ? 1 : 0)>(B, O, P, LY, scratch, queue, ST);
 }
 
 using RefineKernel = void (*)(const DevBatch, const DevOut, const csdo_params, const Layout, double *, int *,
@@ -1149,7 +1253,11 @@ using RefineKernel = void (*)(const DevBatch, const DevOut, const csdo_params, c
 // sub-partition (16384 each): 9 or 10 resident warps put 3 on one sub-partition, i.e. <= 168 per thread.
 static RefineKernel pick_kernel(int block, bool lean) {
 #ifdef CSDO_DEV_FAST  // developer builds: only the two 96-thread variants (short compile)
+#ifdef CSDO_DEV_ONE
+  return dsqp_refine_kernel<96, 2>;
+#else
   return lean ? dsqp_refine_kernel<96, 3> : dsqp_refine_kernel<96, 2>;
+#endif
 #else
   if (block <= 64) return dsqp_refine_kernel<64, 4>;
   if (block <= 96) return lean ? dsqp_refine_kernel<96, 3> : dsqp_refine_kernel<96, 2>;
@@ -1210,16 +1318,16 @@ __global__ void corridors_kernel(const DevBatch B, const csdo_params P, int doub
 // ===================================================================
 // host-side launchers (called from csdo_api.cpp through dsqp_launch.h)
 // ===================================================================
-Layout make_layout(int NT, int KMAX, int tier, int KS) {
+Layout make_layout(int NT, int KMAX, int tier, int KS, int PC) {
   // tier bit 0: per-step row data / row scaling / row state in global scratch instead of shared memory
   // tier bit 1: band factor in global scratch
   Layout l{};
-  l.NT = NT; l.KMAX = KMAX; l.tier = tier; l.KS = KS;
+  l.NT = NT; l.KMAX = KMAX; l.tier = tier; l.KS = KS; l.PC = PC;
   const bool rows_glob = tier & 1, band_glob = tier & 2;
   int o = 0;
   auto take = [&](int n) { int r = o; o += (n + 1) & ~1; return r; };
   l.o_x = take(6 * NT); l.o_D = take(6 * NT); l.o_xt = take(6 * NT); l.o_rhs = take(6 * NT);
-  l.o_carry = take(4 * NT);  // xt | rhs | carry double as factor-time scratch (78 * kMaxP doubles <= 16 NT for NT >= 96)
+  l.o_carry = take(4 * NT);
   if (!rows_glob) {
     l.o_ro = take(RO_COUNT * NT + 8);
     l.o_E = take(16 * NT);
@@ -1227,15 +1335,17 @@ Layout make_layout(int NT, int KMAX, int tier, int KS) {
   }
   l.o_red = take((((NT < 64 ? 64 : NT) + 31) / 32 + 1) * N_COUNT);  // one row per warp + the result row
   l.o_pstart = take((NT + 2 + 1) / 2);
-  l.o_sinv = take(kL2Doubles + 3 * kMaxNs);
-  l.o_L = band_glob ? 0 : take(kLw * 6 * NT + kSkewPad);
+  l.o_sinv = take(pbcr_S_doubles(NT));
+  l.o_L = band_glob ? 0 : take(pbcr_L_doubles(NT));
   l.o_pl = take(PL_COUNT * 4 * KS);
+  l.o_pc = take(PC);
   l.smem_doubles = o;
   size_t g = 0;
   auto gtake = [&](size_t n) { size_t r = g; g += (n + 1) & ~(size_t)1; return r; };
   l.g_cur = gtake(6 * (size_t)NT); l.g_sol = gtake(6 * (size_t)NT); l.g_dy = gtake(16 * (size_t)NT);
   l.g_pl = gtake((size_t)PL_COUNT * 4 * KMAX);
-  l.g_L = gtake((size_t)kLw * 6 * NT + kSkewPad);
+  l.g_pc = gtake((size_t)6 * KMAX);
+  l.g_L = gtake((size_t)pbcr_L_doubles(NT));
   l.g_ro = gtake((size_t)RO_COUNT * NT + 8); l.g_E = gtake(16 * (size_t)NT); l.g_w = gtake(16 * (size_t)NT);
   l.slot_doubles = g;
   return l;
@@ -1293,8 +1403,8 @@ int refine_occupancy(int block, int smem_bytes, bool lean) {
 }
 
 void read_debug_counters(unsigned long long *out16) {
-  cudaMemcpyFromSymbol(out16, g_dbg, 16 * sizeof(unsigned long long));
-  unsigned long long z[16] = {0};
+  cudaMemcpyFromSymbol(out16, g_dbg, 32 * sizeof(unsigned long long));
+  unsigned long long z[32] = {0};
   cudaMemcpyToSymbol(g_dbg, z, sizeof(z));
 }
 

@@ -52,11 +52,12 @@ struct QueueState {
 struct Layout {
   int NT, KMAX, tier, smem_doubles;
   int KS;  // planes per agent that fit the shared-memory plane area
-  int o_x, o_xt, o_rhs, o_D, o_carry, o_red, o_pstart, o_L, o_sinv, o_pl, o_ro, o_E, o_w;
-  size_t g_cur, g_sol, g_dy, g_pl, g_L, g_ro, g_E, g_w, slot_doubles;
+  int PC;  // doubles of the shared-memory plane-contribution buffer (visit_planes)
+  int o_x, o_xt, o_rhs, o_D, o_carry, o_red, o_pstart, o_L, o_sinv, o_pl, o_pc, o_ro, o_E, o_w;
+  size_t g_cur, g_sol, g_dy, g_pl, g_pc, g_L, g_ro, g_E, g_w, slot_doubles;
 };
 
-Layout make_layout(int NT, int KMAX, int tier, int KS);
+Layout make_layout(int NT, int KMAX, int tier, int KS, int PC);
 int refine_occupancy(int block, int smem_bytes, bool lean);
 int refine_kernel_regs(int block, bool lean);
 void read_debug_counters(unsigned long long *out16);
@@ -73,6 +74,11 @@ cudaError_t launch_corridors(const DevBatch &B, const csdo_params &P, int double
 cudaError_t launch_planes_count(const DevBatch &B, const csdo_params &P, int *step_cnt, int *inst_inter_legal,
                                 cudaStream_t stream);
 cudaError_t launch_planes_fill(const DevBatch &B, const csdo_params &P, const int *step_off, int *plane_t,
-                               double *plane_abc, cudaStream_t stream);
+                               double *plane_abc, int *plane_partner, cudaStream_t stream);
+cudaError_t launch_planes_from_pairs(const DevBatch &B, const csdo_params &P, int64_t n_pairs, const int *pairs,
+                                     const int *pos, int *plane_t, double *plane_abc, cudaStream_t stream);
+// exclusive scan of the per-step plane counts on the device (step_cnt [steps + 1], in place)
+cudaError_t launch_plane_offsets(const DevBatch &B, int64_t steps, int *step_cnt, int *tile_sum, int *plane_ptr,
+                                 cudaStream_t stream);
 
 }  // namespace csdo

@@ -82,9 +82,28 @@ __device__ __forceinline__ int find_instance(const DevBatch &B, int a) {
   return lo;
 }
 
+// the two planes of one neighbour pair (calcEqualInterPlanes :71-140): plane_i for agent i, plane_j for j
+__device__ __forceinline__ void pair_planes(const csdo_params &P, const DState &si, const DState &sj, double *oi,
+                                            double *oj) {
+  double a_f2f, b_f2f, c_f2f, c_f2f_, a_f2r, b_f2r, c_f2r, c_f2r_;
+  double a_r2f, b_r2f, c_r2f, c_r2f_, a_r2r, b_r2r, c_r2r, c_r2r_;
+  perpendicular(P.rv, si.xf, si.yf, sj.xf, sj.yf, a_f2f, b_f2f, c_f2f, c_f2f_);
+  perpendicular(P.rv, si.xf, si.yf, sj.xr, sj.yr, a_f2r, b_f2r, c_f2r, c_f2r_);
+  perpendicular(P.rv, si.xr, si.yr, sj.xf, sj.yf, a_r2f, b_r2f, c_r2f, c_r2f_);
+  perpendicular(P.rv, si.xr, si.yr, sj.xr, sj.yr, a_r2r, b_r2r, c_r2r, c_r2r_);
+  if (oi) {
+    oi[0] = a_f2f; oi[1] = b_f2f; oi[2] = c_f2f; oi[3] = a_f2r; oi[4] = b_f2r; oi[5] = c_f2r;
+    oi[6] = a_r2f; oi[7] = b_r2f; oi[8] = c_r2f; oi[9] = a_r2r; oi[10] = b_r2r; oi[11] = c_r2r;
+  }
+  if (oj) {  // its f2r is i's r2f (:131-135)
+    oj[0] = -a_f2f; oj[1] = -b_f2f; oj[2] = -c_f2f_; oj[3] = -a_r2f; oj[4] = -b_r2f; oj[5] = -c_r2f_;
+    oj[6] = -a_f2r; oj[7] = -b_f2r; oj[8] = -c_f2r_; oj[9] = -a_r2r; oj[10] = -b_r2r; oj[11] = -c_r2r_;
+  }
+}
+
 template <bool FILL>
 __global__ void planes_kernel(const DevBatch B, const csdo_params P, int *step_cnt, int *inst_inter_legal,
-                              const int *step_off, int *plane_t, double *plane_abc) {
+                              const int *step_off, int *plane_t, double *plane_abc, int *plane_partner) {
   const int a = blockIdx.x;
   const int inst = find_instance(B, a);
   const int Nt = B.inst_nt[inst];
@@ -110,21 +129,10 @@ __global__ void planes_kernel(const DevBatch B, const csdo_params P, int *step_c
         if (a < b && agent_collision(P, si, sj)) atomicAnd(&inst_inter_legal[inst], 0);
         continue;
       }
-      double a_f2f, b_f2f, c_f2f, c_f2f_, a_f2r, b_f2r, c_f2r, c_f2r_;
-      double a_r2f, b_r2f, c_r2f, c_r2f_, a_r2r, b_r2r, c_r2r, c_r2r_;
-      perpendicular(P.rv, si.xf, si.yf, sj.xf, sj.yf, a_f2f, b_f2f, c_f2f, c_f2f_);
-      perpendicular(P.rv, si.xf, si.yf, sj.xr, sj.yr, a_f2r, b_f2r, c_f2r, c_f2r_);
-      perpendicular(P.rv, si.xr, si.yr, sj.xf, sj.yf, a_r2f, b_r2f, c_r2f, c_r2f_);
-      perpendicular(P.rv, si.xr, si.yr, sj.xr, sj.yr, a_r2r, b_r2r, c_r2r, c_r2r_);
       double *o = plane_abc + (size_t)12 * k;
       plane_t[k] = t;
-      if (a < b) {  // plane_i
-        o[0] = a_f2f; o[1] = b_f2f; o[2] = c_f2f; o[3] = a_f2r; o[4] = b_f2r; o[5] = c_f2r;
-        o[6] = a_r2f; o[7] = b_r2f; o[8] = c_r2f; o[9] = a_r2r; o[10] = b_r2r; o[11] = c_r2r;
-      } else {      // plane_j: its f2r is i's r2f (:131-135)
-        o[0] = -a_f2f; o[1] = -b_f2f; o[2] = -c_f2f_; o[3] = -a_r2f; o[4] = -b_r2f; o[5] = -c_r2f_;
-        o[6] = -a_f2r; o[7] = -b_f2r; o[8] = -c_f2r_; o[9] = -a_r2r; o[10] = -b_r2r; o[11] = -c_r2r_;
-      }
+      if (plane_partner) plane_partner[k] = b;
+      pair_planes(P, si, sj, a < b ? o : nullptr, a < b ? nullptr : o);
       ++k;
     }
     if (!FILL) step_cnt[off + t] = cnt;
@@ -140,14 +148,107 @@ cudaError_t launch_planes_count(const DevBatch &B, const csdo_params &P, int *st
                                 cudaStream_t stream) {
   fill_int_kernel2<<<(B.n_inst + 255) / 256, 256, 0, stream>>>(inst_inter_legal, B.n_inst, 1);
   if (B.n_agents > 0)
-    planes_kernel<false><<<B.n_agents, 128, 0, stream>>>(B, P, step_cnt, inst_inter_legal, nullptr, nullptr, nullptr);
+    planes_kernel<false><<<B.n_agents, 128, 0, stream>>>(B, P, step_cnt, inst_inter_legal, nullptr, nullptr, nullptr, nullptr);
   return cudaGetLastError();
 }
 
 cudaError_t launch_planes_fill(const DevBatch &B, const csdo_params &P, const int *step_off, int *plane_t,
-                               double *plane_abc, cudaStream_t stream) {
+                               double *plane_abc, int *plane_partner, cudaStream_t stream) {
   if (B.n_agents > 0)
-    planes_kernel<true><<<B.n_agents, 128, 0, stream>>>(B, P, nullptr, nullptr, step_off, plane_t, plane_abc);
+    planes_kernel<true><<<B.n_agents, 128, 0, stream>>>(B, P, nullptr, nullptr, step_off, plane_t, plane_abc,
+                                                         plane_partner);
+  return cudaGetLastError();
+}
+
+// calcEqualInterPlanes for an explicit pair list: one thread per pair (t, i, j), i < j global agent ids;
+// pos[2 p], pos[2 p + 1] = plane slots of agent i / agent j (the caller's push order)
+__global__ void planes_from_pairs_kernel(const DevBatch B, const csdo_params P, int64_t n_pairs, const int *pairs,
+                                         const int *pos, int *plane_t, double *plane_abc) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pairs) return;
+  const int t = pairs[3 * p], i = pairs[3 * p + 1], j = pairs[3 * p + 2];
+  const int Nt = (int)(B.agent_off[i + 1] - B.agent_off[i]);
+  const double *gi = B.guess + 6 * B.agent_off[i], *gj = B.guess + 6 * B.agent_off[j];
+  const DState si = make_state(P, gi[t], gi[Nt + t], gi[2 * Nt + t]);
+  const DState sj = make_state(P, gj[t], gj[Nt + t], gj[2 * Nt + t]);
+  const int ki = pos[2 * p], kj = pos[2 * p + 1];
+  plane_t[ki] = t;
+  plane_t[kj] = t;
+  pair_planes(P, si, sj, plane_abc + (size_t)12 * ki, plane_abc + (size_t)12 * kj);
+}
+
+cudaError_t launch_planes_from_pairs(const DevBatch &B, const csdo_params &P, int64_t n_pairs, const int *pairs,
+                                     const int *pos, int *plane_t, double *plane_abc, cudaStream_t stream) {
+  if (n_pairs > 0)
+    planes_from_pairs_kernel<<<(unsigned)((n_pairs + 127) / 128), 128, 0, stream>>>(B, P, n_pairs, pairs, pos, plane_t,
+                                                                                    plane_abc);
+  return cudaGetLastError();
+}
+
+// ---- exclusive scan of the per-step plane counts (device resident, no host round trip) ----
+constexpr int kScanTile = 2048;
+__global__ void scan_tiles_kernel(int *v, int64_t n, int *tile_sum) {
+  __shared__ int ws[8];
+  const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * 8;
+  int x[8], s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { x[i] = base + i < n ? v[base + i] : 0; s += x[i]; }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+  if (lane == 31) ws[warp] = inc;
+  __syncthreads();
+  int woff = 0;
+  for (int w = 0; w < warp; ++w) woff += ws[w];
+  int run = woff + inc - s;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { if (base + i < n) v[base + i] = run; run += x[i]; }
+  if (threadIdx.x == 255) tile_sum[blockIdx.x] = run;
+}
+__global__ void scan_sums_kernel(int *tile_sum, int n_tiles, int *total) {  // one CTA
+  __shared__ int ws[32];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int b0 = 0; b0 < n_tiles; b0 += blockDim.x) {
+    const int i = b0 + threadIdx.x;
+    const int x = i < n_tiles ? tile_sum[i] : 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+    if (lane == 31) ws[warp] = inc;
+    __syncthreads();
+    int woff = 0;
+    for (int w = 0; w < warp; ++w) woff += ws[w];
+    const int c0 = carry;
+    if (i < n_tiles) tile_sum[i] = c0 + woff + inc - x;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = c0 + woff + inc;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry;
+}
+__global__ void scan_add_kernel(int *v, int64_t n, const int *tile_sum, const int *total) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] += tile_sum[i / kScanTile];
+  else if (i == n) v[n] = *total;
+}
+__global__ void plane_ptr_kernel(const int64_t *agent_off, int n_agents, const int *step_off, int *plane_ptr) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a <= n_agents) plane_ptr[a] = step_off[agent_off[a]];
+}
+
+// step_cnt [steps + 1] -> exclusive offsets in place (step_cnt[steps] = total); plane_ptr [n_agents + 1];
+// tile_sum: ceil(steps / 2048) + 1 ints of scratch (the last one receives the total)
+cudaError_t launch_plane_offsets(const DevBatch &B, int64_t steps, int *step_cnt, int *tile_sum, int *plane_ptr,
+                                 cudaStream_t stream) {
+  const int n_tiles = (int)((steps + kScanTile - 1) / kScanTile);
+  if (n_tiles > 0) scan_tiles_kernel<<<n_tiles, 256, 0, stream>>>(step_cnt, steps, tile_sum);
+  scan_sums_kernel<<<1, 1024, 0, stream>>>(tile_sum, n_tiles, tile_sum + n_tiles);
+  scan_add_kernel<<<(unsigned)((steps + 1 + 255) / 256), 256, 0, stream>>>(step_cnt, steps, tile_sum, tile_sum + n_tiles);
+  plane_ptr_kernel<<<(B.n_agents + 1 + 255) / 256, 256, 0, stream>>>(B.agent_off, B.n_agents, step_cnt, plane_ptr);
   return cudaGetLastError();
 }
 

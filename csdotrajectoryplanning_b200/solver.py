@@ -67,6 +67,37 @@ class DsqpSolver:
                                                  dbatch.max_nt, dbatch.max_planes,
                                                  C.c_void_p(stream_ptr) if stream_ptr else None))
 
+    def sync(self) -> None:
+        """csdo_sync: waits for the last refine_device and raises if the device flagged an error."""
+        self._check(self._lib.csdo_sync(self._h))
+
+    # -- pre-process on tensors resident in HBM (csdo_planes_*_device) ------
+    def planes_device(self, dbatch: "DeviceBatch", stream_ptr: int = 0, partners: bool = False):
+        """findNeighborPairsByTrustRegion + calcEqualInterPlanes on a DeviceBatch: plane_ptr / plane_t /
+        plane_abc are created on the device (no host round trip except the plane count) and attached to
+        `dbatch`.  Returns (inst_inter_legal tensor, plane_partner tensor or None)."""
+        import torch
+        b = dbatch.host
+        dev = dbatch.t["guess"].device
+        steps, A, I = b.total_steps, b.n_agents, b.n_inst
+        step_off = torch.empty(steps + 1, dtype=torch.int32, device=dev)
+        plane_ptr = torch.zeros(A + 1, dtype=torch.int32, device=dev)
+        legal = torch.ones(max(I, 1), dtype=torch.int32, device=dev)
+        total = C.c_int64(0)
+        sp = C.c_void_p(stream_ptr) if stream_ptr else None
+        self._check(self._lib.csdo_planes_count_device(self._h, C.byref(dbatch.c), steps, step_off.data_ptr(),
+                                                       plane_ptr.data_ptr(), legal.data_ptr(), C.byref(total), sp))
+        n = int(total.value)
+        plane_t = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        plane_abc = torch.empty(12 * max(n, 1), dtype=torch.float64, device=dev)
+        partner = torch.empty(max(n, 1), dtype=torch.int32, device=dev) if partners else None
+        if n:
+            self._check(self._lib.csdo_planes_fill_device(self._h, C.byref(dbatch.c), step_off.data_ptr(),
+                                                          plane_t.data_ptr(), plane_abc.data_ptr(),
+                                                          partner.data_ptr() if partners else None, sp))
+        dbatch.set_planes(plane_ptr, plane_t[:n], plane_abc[:12 * n])
+        return legal[:I], (partner[:n] if partners else None)
+
     # -- corridors only (csdo_corridors) -----------------------------------
     def corridors(self, batch: Batch, double_centres: bool = False):
         S = batch.total_steps
@@ -120,6 +151,24 @@ class DeviceBatch:
     def h2d_bytes(self) -> int:
         return int(sum(t.numel() * t.element_size() for t in self.t.values()))
 
+    def set_planes(self, plane_ptr, plane_t, plane_abc) -> None:
+        """Attach device-resident planes (DsqpSolver.planes_device) and the processing order they imply."""
+        import torch
+        self.t["plane_ptr"], self.t["plane_t"], self.t["plane_abc"] = plane_ptr, plane_t, plane_abc
+        k = torch.diff(plane_ptr.to(torch.int64))
+        self.max_planes = int(k.max().item()) if k.numel() else 0
+        nt = torch.from_numpy(self.host.agent_nt()).to(plane_ptr.device)
+        cost = 13 * nt + 4 * k
+        self.t["agent_order"] = torch.argsort(-cost, stable=True).to(torch.int32)
+        for name in ("plane_ptr", "plane_t", "plane_abc", "agent_order"):
+            ten = self.t[name]
+            setattr(self.c, name, ten.data_ptr() if ten.numel() else None)
+
+    def planes_to_host(self) -> Batch:
+        """The batch with the device-built planes copied back (for checks against the oracle)."""
+        return self.host.with_planes(self.t["plane_ptr"].cpu().numpy(), self.t["plane_t"].cpu().numpy(),
+                                     self.t["plane_abc"].cpu().numpy())
+
 
 class DeviceResult:
     def __init__(self, batch: Batch, device):
@@ -136,6 +185,10 @@ class DeviceResult:
 
     def to_host(self) -> RefineResult:
         return RefineResult(**{k: v.cpu().numpy() for k, v in self.t.items()})
+
+    def counters_to_host(self) -> dict:
+        """Only the small per-agent / per-instance arrays (no trajectories)."""
+        return {k: v.cpu().numpy() for k, v in self.t.items() if k not in ("traj", "corridors")}
 
 
 # ---------------------------------------------------------------------------

@@ -1,30 +1,47 @@
 // Drop-in C++ interface of the DSQP refine stage on top of the C ABI
 // (include/csdo_dsqp.h).  Header-only; link with libcsdo_dsqp.so.
 //
-// It keeps the reference's own class and type names for this path so that the
-// caller in csdo.cc:113-167 compiles unchanged against it:
-//   OptimizeResult, QpParm            sqp/common.h:14-22, 39-52
-//   Corridor                          sqp/corridor.h:8-11
-//   InterPlane                        sqp/inter_agent_cons.h:47-63
-//   Location                          common/motion_planning.h:80-97
-//   findNeighborPairsByTrustRegion    sqp/inter_agent_cons.h:40-45
-//   calcEqualInterPlanes              sqp/inter_agent_cons.h:70-73
-//   SolverDSQP                        sqp/dsqp_solver.h:24-47 (constructor does the work)
-// Differences that a maintainer has to know are listed in INTEGRATION.md: no
-// Eigen/OSQP types (solveOSQP is gone), obstacles may be any iterable of
-// Location (std::unordered_set<Location> included), and one extra optional
-// constructor argument carries the vehicle constants that the reference keeps
-// in the global `Constants` class.
+// Two modes.
+//  * INSIDE THE REFERENCE TREE (define CSDO_WITH_REFERENCE_TYPES before the include, with the reference
+//    root on the include path): the header uses the reference's OWN types --
+//    libMultiRobotPlanning::{OptimizeResult, QpParm, Corridor, InterPlane} and the global Location with
+//    its std::hash (common/motion_planning.h:80-109, sqp/common.h:14-52, sqp/corridor.h:8-11,
+//    sqp/inter_agent_cons.h:47-63) -- and adds only
+//        class SolverDSQP                                   sqp/dsqp_solver.h:24-47 (constructor = refine)
+//        csdo_b200::findNeighborPairsByTrustRegion          sqp/inter_agent_cons.h:40-45 (same arguments)
+//        csdo_b200::calcEqualInterPlanes                    sqp/inter_agent_cons.h:70-73 (same arguments)
+//        csdo_b200::buildInterPlanes                        both in one call
+//    so csdo.cc compiles with `#include "sqp/dsqp_solver.h"` replaced by this header (INTEGRATION.md shows
+//    the diff; tests/cpp/ref_tree_compile.cpp is csdo.cc:111-167 built that way).  InterpolateInitalGuess
+//    and dumpSolutions stay the reference's own (sqp/inter_agent_cons.cc needs neither Eigen nor OSQP).
+//  * STANDALONE (default): the same type names with the same fields are defined here, Location gets
+//    operator< / operator== and std::hash<Location>, and the two plane functions are also visible in
+//    namespace libMultiRobotPlanning under the reference's names.
+// Differences a maintainer has to know are listed in INTEGRATION.md: no Eigen/OSQP types (solveOSQP is
+// gone), obstacles may be any iterable of Location (std::unordered_set<Location> included), and one
+// extra optional constructor argument carries the vehicle constants that the reference keeps in the
+// global `Constants` class.
 #pragma once
 
+#include <algorithm>
 #include <array>
 #include <chrono>
 #include <cstdint>
+#include <cstring>
+#include <functional>
 #include <stdexcept>
 #include <string>
+#include <tuple>
+#include <unordered_set>
 #include <vector>
 
 #include "../csdo_dsqp.h"
+
+#if defined(CSDO_WITH_REFERENCE_TYPES)
+#include "common/motion_planning.h"
+#include "sqp/common.h"
+#include "sqp/corridor.h"  // pulls sqp/inter_agent_cons.h (InterPlane, InterpolateInitalGuess, dumpSolutions)
+#else
 
 namespace libMultiRobotPlanning {
 
@@ -61,8 +78,22 @@ struct InterPlane {  // sqp/inter_agent_cons.h:47-63
 struct Location {  // common/motion_planning.h:80-97
   Location(double x, double y, double r) : x(x), y(y), r(r) {}
   double x, y, r;
-  bool operator==(const Location &o) const { return x == o.x && y == o.y && r == o.r; }
+  bool operator<(const Location &o) const { return std::tie(x, y, r) < std::tie(o.x, o.y, o.r); }
+  bool operator==(const Location &o) const { return std::tie(x, y, r) == std::tie(o.x, o.y, o.r); }
 };
+
+namespace std {
+template <>
+struct hash<Location> {  // common/motion_planning.h:99-109 hashes (x, y); any mix of the two serves here
+  size_t operator()(const Location &s) const {
+    size_t seed = std::hash<double>()(s.x);
+    seed ^= std::hash<double>()(s.y) + 0x9e3779b97f4a7c15ull + (seed << 6) + (seed >> 2);
+    return seed;
+  }
+};
+}  // namespace std
+
+#endif  // CSDO_WITH_REFERENCE_TYPES
 
 namespace csdo_detail {
 
@@ -113,17 +144,35 @@ inline void pack_guess(const std::vector<std::vector<OptimizeResult>> &x0_bar, P
 
 }  // namespace csdo_detail
 
-namespace libMultiRobotPlanning {
+namespace csdo_b200 {
 
-// findNeighborPairsByTrustRegion + calcEqualInterPlanes in one call (the pair list itself is only an
-// intermediate of the reference, csdo.cc:119-129).  Returns initial_inter_legal.
-inline bool buildInterPlanes(const std::vector<std::vector<OptimizeResult>> &x0_bar,
-                             std::vector<std::vector<InterPlane>> &inter_planes, const csdo_params *params = nullptr,
-                             int device = 0) {
-  csdo_detail::Packed p;
+using libMultiRobotPlanning::InterPlane;
+using libMultiRobotPlanning::OptimizeResult;
+
+namespace detail {
+inline csdo_params plane_params(const csdo_params *params, const double *r_trust, const double *rv) {
+  csdo_params P;
+  if (params) P = *params; else csdo_default_params(&P);
+  if (r_trust) P.r_trust = *r_trust;
+  if (rv) P.rv = *rv;
+  return P;
+}
+inline void unpack_planes(const csdo_detail::Packed &p, std::vector<std::vector<InterPlane>> &inter_planes) {
+  const int Na = p.inst_agent_ptr[1];
+  inter_planes.assign(Na, {});
+  for (int a = 0; a < Na; ++a)
+    for (int k = p.plane_ptr[a]; k < p.plane_ptr[a + 1]; ++k) {
+      const double *q = p.plane_abc.data() + (size_t)12 * k;
+      inter_planes[a].push_back(InterPlane{p.plane_t[k], q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7], q[8], q[9],
+                                           q[10], q[11]});
+    }
+}
+// count + fill through the C ABI; partner (optional) receives the other agent of every plane
+inline bool build(const std::vector<std::vector<OptimizeResult>> &x0_bar, const csdo_params &P, int device,
+                  csdo_detail::Packed &p, std::vector<int32_t> *partner) {
   csdo_detail::pack_guess(x0_bar, p);
   csdo_handle *h = nullptr;
-  csdo_detail::check(csdo_create(params, device, &h), nullptr, "csdo_create");
+  csdo_detail::check(csdo_create(&P, device, &h), nullptr, "csdo_create");
   const int Na = p.inst_agent_ptr[1];
   int32_t legal = 1;
   csdo_batch b = p.view();
@@ -132,20 +181,76 @@ inline bool buildInterPlanes(const std::vector<std::vector<OptimizeResult>> &x0_
     const int total = p.plane_ptr[Na];
     p.plane_t.assign(total, 0);
     p.plane_abc.assign((size_t)12 * total, 0.0);
-    csdo_detail::check(csdo_planes_fill(h, &b, p.plane_ptr.data(), p.plane_t.data(), p.plane_abc.data()), h,
-                       "csdo_planes_fill");
+    if (partner) partner->assign(total, 0);
+    csdo_detail::check(csdo_planes_fill_partners(h, &b, p.plane_ptr.data(), p.plane_t.data(), p.plane_abc.data(),
+                                                 partner ? partner->data() : nullptr),
+                       h, "csdo_planes_fill");
   } catch (...) { csdo_destroy(h); throw; }
   csdo_destroy(h);
-  inter_planes.assign(Na, {});
-  for (int a = 0; a < Na; ++a)
-    for (int k = p.plane_ptr[a]; k < p.plane_ptr[a + 1]; ++k) {
-      const double *q = p.plane_abc.data() + (size_t)12 * k;
-      inter_planes[a].push_back(InterPlane{p.plane_t[k], q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7], q[8], q[9],
-                                           q[10], q[11]});
-    }
   return legal != 0;
 }
+}  // namespace detail
 
+// findNeighborPairsByTrustRegion (sqp/inter_agent_cons.cc:12-49), same arguments and result: the list of
+// (t, i, j), i < j, in (t, i, j)-lexicographic order, and initial_inter_legal.
+inline bool findNeighborPairsByTrustRegion(const std::vector<std::vector<OptimizeResult>> &solution, const double &r,
+                                           const double &rv, std::vector<std::array<int, 3>> &neighbor_pairs,
+                                           const csdo_params *vehicle = nullptr, int device = 0) {
+  csdo_detail::Packed p;
+  std::vector<int32_t> partner;
+  const bool legal = detail::build(solution, detail::plane_params(vehicle, &r, &rv), device, p, &partner);
+  neighbor_pairs.clear();
+  const int Na = p.inst_agent_ptr[1];
+  for (int a = 0; a < Na; ++a)
+    for (int k = p.plane_ptr[a]; k < p.plane_ptr[a + 1]; ++k)
+      if (a < partner[k]) neighbor_pairs.push_back(std::array<int, 3>{p.plane_t[k], a, partner[k]});
+  std::sort(neighbor_pairs.begin(), neighbor_pairs.end());
+  return legal;
+}
+
+// calcEqualInterPlanes (sqp/inter_agent_cons.cc:71-140), same arguments: the planes of the listed pairs,
+// pushed to both agents in list order.
+inline void calcEqualInterPlanes(const std::vector<std::vector<OptimizeResult>> &x0_bar,
+                                 const std::vector<std::array<int, 3>> &neighbor_pairs,
+                                 std::vector<std::vector<InterPlane>> &inter_planes,
+                                 const csdo_params *vehicle = nullptr, int device = 0) {
+  csdo_detail::Packed p;
+  csdo_detail::pack_guess(x0_bar, p);
+  const csdo_params P = detail::plane_params(vehicle, nullptr, nullptr);
+  std::vector<int32_t> flat((size_t)3 * neighbor_pairs.size());
+  for (size_t q = 0; q < neighbor_pairs.size(); ++q)
+    for (int e = 0; e < 3; ++e) flat[3 * q + e] = neighbor_pairs[q][e];
+  p.plane_t.assign(2 * neighbor_pairs.size(), 0);
+  p.plane_abc.assign((size_t)24 * neighbor_pairs.size(), 0.0);
+  csdo_handle *h = nullptr;
+  csdo_detail::check(csdo_create(&P, device, &h), nullptr, "csdo_create");
+  csdo_batch b = p.view();
+  const int rc = csdo_planes_from_pairs(h, &b, (int64_t)neighbor_pairs.size(), flat.data(), p.plane_ptr.data(),
+                                        p.plane_t.data(), p.plane_abc.data());
+  if (rc != CSDO_OK) { std::string e = csdo_last_error(h); csdo_destroy(h); throw std::runtime_error("csdo_planes_from_pairs: " + e); }
+  csdo_destroy(h);
+  detail::unpack_planes(p, inter_planes);
+}
+
+// both in one call (the pair list is only an intermediate of the reference, csdo.cc:119-129).
+// Returns initial_inter_legal.
+inline bool buildInterPlanes(const std::vector<std::vector<OptimizeResult>> &x0_bar,
+                             std::vector<std::vector<InterPlane>> &inter_planes, const csdo_params *params = nullptr,
+                             int device = 0) {
+  csdo_detail::Packed p;
+  const bool legal = detail::build(x0_bar, detail::plane_params(params, nullptr, nullptr), device, p, nullptr);
+  detail::unpack_planes(p, inter_planes);
+  return legal;
+}
+
+}  // namespace csdo_b200
+
+namespace libMultiRobotPlanning {
+using csdo_b200::buildInterPlanes;
+#if !defined(CSDO_WITH_REFERENCE_TYPES)
+using csdo_b200::calcEqualInterPlanes;
+using csdo_b200::findNeighborPairsByTrustRegion;
+#endif
 }  // namespace libMultiRobotPlanning
 
 class SolverDSQP {

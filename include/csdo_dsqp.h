@@ -166,6 +166,14 @@ int csdo_refine(csdo_handle *h, const csdo_batch *in, csdo_result *out);
 int csdo_refine_device(csdo_handle *h, const csdo_batch *in, csdo_result *out,
                        int max_nt, int max_planes, void *cuda_stream);
 
+/* Waits for the last csdo_refine_device of this handle and reports what only
+ * the device knows: CSDO_ERR_INVALID if an agent had more planes than the
+ * max_planes passed (its result is then invalid), CSDO_ERR_CUDA if the work
+ * queue stalled.  A handle owns ONE scratch area and work queue: calls on the
+ * same handle must be ordered on one stream (or separated by csdo_sync); use
+ * one handle per concurrent stream. */
+int csdo_sync(csdo_handle *h);
+
 /* Kernel-launch and timing facts of the last refine on this handle
  * (launches: kernels enqueued; smem_bytes/block/grid: the DSQP kernel's
  * configuration; tier: 0 all-shared, 1 read-only rows in global, 2 band
@@ -200,6 +208,38 @@ int csdo_planes_count(csdo_handle *h, const csdo_batch *in, int32_t *plane_ptr,
 int csdo_planes_fill(csdo_handle *h, const csdo_batch *in,
                      const int32_t *plane_ptr, int32_t *plane_t,
                      double *plane_abc);
+/* Same, and plane_partner[k] (may be NULL) receives the global id of the other
+ * agent of plane k: the pair list of findNeighborPairsByTrustRegion
+ * (inter_agent_cons.cc:12-49) is {(plane_t[k], a, partner[k]) : a < partner[k]}
+ * sorted by (t, a, partner). */
+int csdo_planes_fill_partners(csdo_handle *h, const csdo_batch *in,
+                              const int32_t *plane_ptr, int32_t *plane_t,
+                              double *plane_abc, int32_t *plane_partner);
+
+/* calcEqualInterPlanes (inter_agent_cons.cc:71-140) for an explicit pair list:
+ * pairs[p] = {t, i, j} with global agent ids i, j of one instance.  Every pair
+ * pushes one plane to agent i and one to agent j, in list order.  HOST pointers;
+ * plane_ptr [n_agents+1] out, plane_t [2 n_pairs], plane_abc [2 n_pairs][12]. */
+int csdo_planes_from_pairs(csdo_handle *h, const csdo_batch *in, int64_t n_pairs,
+                           const int32_t *pairs, int32_t *plane_ptr,
+                           int32_t *plane_t, double *plane_abc);
+
+/* Device-resident pre-process (every pointer a DEVICE pointer, enqueued on
+ * cuda_stream, NULL = the handle's stream; in->plane_* ignored).
+ * count: step_off [total_steps+1] receives the index of the first plane of
+ * every (agent, step) (exclusive scan on the device; the last entry is the
+ * total), plane_ptr [n_agents+1], inst_inter_legal [n_inst].  If total_planes
+ * (a HOST pointer) is non-NULL the call synchronizes and stores the plane
+ * count there so that the caller can size plane_t / plane_abc.
+ * fill: plane_t [total], plane_abc [total][12], plane_partner [total] or NULL. */
+int csdo_planes_count_device(csdo_handle *h, const csdo_batch *in, int64_t total_steps,
+                             int32_t *step_off, int32_t *plane_ptr,
+                             int32_t *inst_inter_legal, int64_t *total_planes,
+                             void *cuda_stream);
+int csdo_planes_fill_device(csdo_handle *h, const csdo_batch *in,
+                            const int32_t *step_off, int32_t *plane_t,
+                            double *plane_abc, int32_t *plane_partner,
+                            void *cuda_stream);
 
 /*
  * Measurement helper (no reference counterpart): sustained FP64 FMA throughput

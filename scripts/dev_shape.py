@@ -45,3 +45,5 @@ print(json.dumps({"workload": name, "instances": len(inst), "agents": int(b.n_ag
                   "tflops": fl / dt * 1e-12, "refine_ms_per_instance": 1e3 * dt / len(inst),
                   "status_hist": {int(k): int(v) for k, v in zip(*np.unique(res.status, return_counts=True))},
                   "launch": S.last_launch()}))
+if os.environ.get("CSDO_PROFILE"):   # -DCSDO_DEV_TIMERS build: the host-pointer call prints the phase timers
+    S.refine(b)

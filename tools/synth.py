@@ -44,7 +44,7 @@ def synth_instance(seed: int, size: float, n_agents: int, n_obs: int, n_actions:
     nt_cap = 3 * n_actions[1] + 1
     guess = np.zeros((n_agents, 6, nt_cap))
     obs = np.zeros((max(n_obs, 1), 3))
-    nt, no = C.c_int(0), C.c_int(0)
+    nt, no = C.c_int(0), C.c_int(0)   # obs_radius < 0: room-like wall layout with discs of radius -obs_radius
     rc = L.synth_instance(seed, size, n_agents, n_obs, n_actions[0], n_actions[1], obs_radius, params.f2x,
                           params.r2x, params.rv, params.dt, params.LF, params.LB, guess.ctypes.data, nt_cap,
                           C.byref(nt), obs.ctypes.data, C.byref(no))
@@ -54,6 +54,13 @@ def synth_instance(seed: int, size: float, n_agents: int, n_obs: int, n_actions:
     return Instance(g, size, size, obs[: no.value].copy(), None, None, name or f"synth_{seed}")
 
 
+def synth_jobs(jobs, params, threads: Optional[int] = None) -> List:
+    """jobs: (seed, size, n_agents, n_obs, (min, max) actions, name, obs_radius)"""
+    lib()
+    with ThreadPoolExecutor(threads or min(32, os.cpu_count() or 1)) as ex:   # ctypes releases the GIL
+        return list(ex.map(lambda a: synth_instance(a[0], a[1], a[2], a[3], a[4], params, a[5], a[6]), jobs))
+
+
 def synth_batch(shapes: Sequence[Tuple[float, int, int, Tuple[int, int]]], per_shape: int, seed: int, params,
                 threads: Optional[int] = None) -> List:
     """shapes: (map size, n_agents, n_obstacles, (min, max) coarse actions); per_shape instances of each."""
@@ -61,13 +68,34 @@ def synth_batch(shapes: Sequence[Tuple[float, int, int, Tuple[int, int]]], per_s
     k = 0
     for (size, na, no, nact) in shapes:
         for j in range(per_shape):
-            jobs.append((seed + k, size, na, no, nact, f"map{int(size)}_a{na}_o{no}_n{nact[1]}_ex{j}"))
+            jobs.append((seed + k, size, na, no, nact, f"map{int(size)}_a{na}_o{no}_n{nact[1]}_ex{j}", 0.8))
             k += 1
-    lib()
-    with ThreadPoolExecutor(threads or min(32, os.cpu_count() or 1)) as ex:   # ctypes releases the GIL
-        return list(ex.map(lambda a: synth_instance(a[0], a[1], a[2], a[3], a[4], params, a[5]), jobs))
+    return synth_jobs(jobs, params, threads)
+
+
+def workload_jobs(name: str, total: int, seed: int = 1234):
+    """The job list of a named bench workload; instance i is the same whatever the rank count.
+    c5          BASELINE configs[4]: 100x100, 100 agents, 50 obstacles, horizons 127 / 190 / 256 in turn
+    map100_a100 BASELINE configs[2]: benchmark/map100by100/agents100/obstacle shape (60 instances there)
+    room        BASELINE configs[3]: benchmark/room shape: 100x100, agents 10..50, 130..298 wall discs r = 0.5
+    map50       BASELINE configs[1]: the map50by50 sweep, agents 5..25 x {empty, 25 obstacles}
+    """
+    jobs = []
+    for i in range(total):
+        if name == "c5":
+            size, na, no, nact, rad = C5_SHAPES[i % 3] + (0.8,)
+        elif name == "map100_a100":
+            size, na, no, nact, rad = 100.0, 100, 50, (40, 58), 0.8
+        elif name == "room":
+            size, na, no, nact, rad = 100.0, (10, 20, 30, 40, 50)[i % 5], 130 + (37 * i) % 169, (36, 55), -0.5
+        elif name == "map50":
+            size, na, no, nact, rad = 50.0, (5, 10, 15, 20, 25)[i % 5], (0, 25)[(i // 5) % 2], (12, 30), 0.8
+        else:
+            raise ValueError(name)
+        jobs.append((seed + i, size, na, no, nact, f"{name}_{i}", rad))
+    return jobs
 
 
 # BASELINE.json configs[4]: 100x100 maps, 100 agents (the largest benchmark agent count), 50 obstacles,
-# horizons 127 / 193 / 256 (Nt in {128, 192, 256})
-C5_SHAPES = [(100.0, 100, 50, (28, 42)), (100.0, 100, 50, (43, 64)), (100.0, 100, 50, (57, 85))]
+# horizons 127 / 190 / 256 (SURVEY section 8d: Nt in {128, 192, 256}; a horizon is 3 x coarse actions + 1)
+C5_SHAPES = [(100.0, 100, 50, (28, 42)), (100.0, 100, 50, (43, 63)), (100.0, 100, 50, (57, 85))]

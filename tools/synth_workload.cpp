@@ -99,6 +99,26 @@ int synth_instance(uint64_t seed, double size, int n_agents, int n_obs, int act_
   Rng rng(seed);
   Gen g{size, f2x, r2x, rv, {}, {}};
   int tries = 0;
+  if (obs_radius < 0) {
+    // room-like map (benchmark/room: 100x100, 130..300 discs of r = 0.5 on the integer grid, laid out as
+    // wall segments with door gaps): horizontal / vertical walls on a 10 m lattice until n_obs discs exist
+    const double r = -obs_radius;
+    int guard = 0;
+    while ((int)g.obs.size() / 3 < n_obs && guard++ < 400) {
+      const bool horiz = rng.uniform() < 0.5;
+      const int line = 10 * (1 + rng.below((int)(size / 10) - 1));        // wall position
+      const int a0 = rng.below((int)size - 10), len = 10 + rng.below(31);  // start and length along the wall
+      const int door = a0 + 3 + rng.below(len > 8 ? len - 6 : 1);          // a 6 m door gap
+      for (int a = a0; a <= a0 + len && a <= (int)size && (int)g.obs.size() / 3 < n_obs; ++a) {
+        if (a >= door && a < door + 6) continue;
+        const double x = horiz ? a : line, y = horiz ? line : a;
+        bool dup = false;
+        for (size_t o = 0; o + 2 < g.obs.size(); o += 3) if (g.obs[o] == x && g.obs[o + 1] == y) { dup = true; break; }
+        if (!dup) { g.obs.push_back(x); g.obs.push_back(y); g.obs.push_back(r); }
+      }
+    }
+    n_obs = 0;  // (skip the uniform placement below)
+  }
   while ((int)g.obs.size() / 3 < n_obs && tries < 100 * (n_obs > 0 ? n_obs : 1)) {  // generate_scenarios.py:83-102
     ++tries;
     const double x = rng.uniform(obs_radius, size - obs_radius), y = rng.uniform(obs_radius, size - obs_radius);
