@@ -21,7 +21,7 @@ class CsdoBatch(C.Structure):
         ("inst_dims", C.c_void_p), ("obs_ptr", C.c_void_p), ("obs", C.c_void_p),
         ("agent_off", C.c_void_p), ("guess", C.c_void_p),
         ("plane_ptr", C.c_void_p), ("plane_t", C.c_void_p), ("plane_abc", C.c_void_p),
-        ("agent_order", C.c_void_p),
+        ("agent_order", C.c_void_p), ("n_active", C.c_int32),
     ]
 
 
@@ -77,6 +77,8 @@ class Batch:
     plane_t: np.ndarray
     plane_abc: np.ndarray
     names: List[str] = field(default_factory=list)
+    agent_order: Optional[np.ndarray] = None   # int32 processing order; with n_active > 0: the active subset
+    n_active: int = 0
 
     @property
     def n_inst(self) -> int:
@@ -122,7 +124,13 @@ class Batch:
             arr = getattr(self, name)
             assert arr.flags["C_CONTIGUOUS"]
             setattr(b, name, arr.ctypes.data if arr.size else None)
-        b.agent_order = None
+        if self.agent_order is not None:
+            assert self.agent_order.dtype == np.int32 and self.agent_order.flags["C_CONTIGUOUS"]
+            b.agent_order = self.agent_order.ctypes.data
+            b.n_active = int(self.n_active)
+        else:
+            b.agent_order = None
+            b.n_active = 0
         return b
 
     def select_instances(self, idx: Sequence[int]) -> "Batch":

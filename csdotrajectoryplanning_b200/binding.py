@@ -23,7 +23,7 @@ EXPORTS = [
     "csdo_default_params", "csdo_version", "csdo_create", "csdo_destroy", "csdo_last_error",
     "csdo_refine", "csdo_refine_device", "csdo_last_launch", "csdo_corridors",
     "csdo_planes_count", "csdo_planes_fill", "csdo_planes_fill_partners", "csdo_planes_from_pairs",
-    "csdo_planes_count_device", "csdo_planes_fill_device", "csdo_sync", "csdo_measure_fp64_peak",
+    "csdo_planes_count_device", "csdo_planes_fill_device", "csdo_sync", "csdo_aggregate_status_device", "csdo_measure_fp64_peak",
 ]
 
 _lib = None
@@ -77,6 +77,8 @@ def lib():
         L.csdo_planes_fill_device.argtypes = [H, C.POINTER(CsdoBatch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                               C.c_void_p]
         L.csdo_planes_fill_device.restype = C.c_int
+        L.csdo_aggregate_status_device.argtypes = [H, C.POINTER(CsdoBatch), C.POINTER(CsdoResult), C.c_void_p]
+        L.csdo_aggregate_status_device.restype = C.c_int
         L.csdo_sync.argtypes = [H]
         L.csdo_sync.restype = C.c_int
         L.csdo_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]

@@ -108,9 +108,12 @@ int validate_host(csdo_handle *h, const csdo_batch *in, bool need_planes, Meta &
       }
     }
   }
-  if (in->agent_order) {  // must be a permutation: a duplicate would let two CTAs refine one agent
+  if (in->n_active < 0 || in->n_active > in->n_agents || (in->n_active > 0 && !in->agent_order)) {
+    h->err = "n_active needs agent_order and 0 <= n_active <= n_agents"; return CSDO_ERR_INVALID;
+  }
+  if (in->agent_order) {  // distinct ids in range: a duplicate would let two CTAs refine one agent
     std::vector<char> seen((size_t)in->n_agents, 0);
-    for (int a = 0; a < in->n_agents; ++a) {
+    for (int a = 0; a < (in->n_active > 0 ? in->n_active : in->n_agents); ++a) {
       const int v = in->agent_order[a];
       if (v < 0 || v >= in->n_agents || seen[v]) { h->err = "agent_order is not a permutation"; return CSDO_ERR_INVALID; }
       seen[v] = 1;
@@ -157,7 +160,7 @@ int upload_batch(csdo_handle *h, const csdo_batch *in, const Meta &m, bool plane
   if ((rc = upload(h, 4, in->obs, (size_t)3 * m.n_obs, &B.obs))) return rc;
   if ((rc = upload(h, 5, in->agent_off, (size_t)in->n_agents + 1, &B.agent_off))) return rc;
   if ((rc = upload(h, 6, in->guess, (size_t)6 * m.steps, &B.guess))) return rc;
-  B.plane_ptr = nullptr; B.plane_t = nullptr; B.plane_abc = nullptr; B.agent_order = nullptr;
+  B.plane_ptr = nullptr; B.plane_t = nullptr; B.plane_abc = nullptr; B.agent_order = nullptr; B.n_active = 0;
   if (planes) {
     if ((rc = upload(h, 7, in->plane_ptr, (size_t)in->n_agents + 1, &B.plane_ptr))) return rc;
     if ((rc = upload(h, 8, in->plane_t, (size_t)m.n_planes, &B.plane_t))) return rc;
@@ -173,6 +176,7 @@ DevBatch as_dev(const csdo_batch *in) {
   B.obs_ptr = in->obs_ptr; B.obs = in->obs; B.agent_off = in->agent_off; B.guess = in->guess;
   B.plane_ptr = in->plane_ptr; B.plane_t = in->plane_t; B.plane_abc = in->plane_abc;
   B.agent_order = in->agent_order;
+  B.n_active = in->agent_order ? in->n_active : 0;
   return B;
 }
 
@@ -216,7 +220,8 @@ int run_refine(csdo_handle *h, const DevBatch &B, const DevOut &O, int max_nt, i
   }
   if (occ < 1) { h->err = "horizon does not fit the kernel's shared-memory layout"; return CSDO_ERR_UNSUPPORTED; }
   if (const char *cap = getenv("CSDO_MAX_CTAS_PER_SM")) occ = std::max(1, std::min(occ, atoi(cap)));  // developer knob
-  const int grid = std::min(B.n_agents, h->num_sms * occ);
+  const int n_work = (B.n_active > 0 && B.agent_order) ? B.n_active : B.n_agents;
+  const int grid = std::min(n_work, h->num_sms * occ);
   int rc;
   if ((rc = ensure(h, h->scratch, (size_t)grid * LY.slot_doubles * sizeof(double)))) return rc;
   if ((rc = ensure(h, h->queue, 2048))) return rc;
@@ -325,6 +330,18 @@ int csdo_refine_device(csdo_handle *h, const csdo_batch *in, csdo_result *out, i
   return run_refine(h, B, O, max_nt, max_planes, s);
 }
 
+int csdo_aggregate_status_device(csdo_handle *h, const csdo_batch *in, csdo_result *out, void *cuda_stream) {
+  if (!h || !in || !out || !out->status || !out->inst_status || !in->inst_agent_ptr) return CSDO_ERR_INVALID;
+  DeviceGuard guard(h->device);
+  cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->stream;
+  if (in->n_inst == 0) return CSDO_OK;
+  DevBatch B = as_dev(in);
+  DevOut O{out->traj, out->corridors, out->status, out->sqp_iters, out->n_qp, out->admm_iters,
+           out->n_factor, out->objective, out->inst_status, out->inst_static_legal};
+  if (set_err(h, "aggregate_status", launch_aggregate_status(B, O, s))) return CSDO_ERR_CUDA;
+  return CSDO_OK;
+}
+
 int csdo_sync(csdo_handle *h) {
   if (!h) return CSDO_ERR_INVALID;
   DeviceGuard guard(h->device);
@@ -350,7 +367,8 @@ int csdo_refine(csdo_handle *h, const csdo_batch *in, csdo_result *out) {
   if ((rc = upload_batch(h, in, m, true, B))) return rc;
   // processing order: longest problems first (unless the caller gave one)
   std::vector<int> order(in->n_agents);
-  if (in->agent_order) std::copy(in->agent_order, in->agent_order + in->n_agents, order.begin());
+  const int n_listed = in->n_active > 0 ? in->n_active : in->n_agents;
+  if (in->agent_order) std::copy(in->agent_order, in->agent_order + n_listed, order.begin());
   else {
     std::iota(order.begin(), order.end(), 0);
     std::vector<int64_t> cost(in->n_agents);
@@ -359,6 +377,7 @@ int csdo_refine(csdo_handle *h, const csdo_batch *in, csdo_result *out) {
     std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cost[x] > cost[y]; });
   }
   if ((rc = upload(h, 10, order.data(), order.size(), &B.agent_order))) return rc;
+  B.n_active = in->agent_order ? in->n_active : 0;
   DevOut O;
   const size_t A = in->n_agents, I = in->n_inst;
   if ((rc = devalloc(h, 11, 6 * (size_t)m.steps, &O.traj))) return rc;
@@ -434,7 +453,7 @@ int csdo_planes_count_device(csdo_handle *h, const csdo_batch *in, int64_t total
   const int n_tiles = (int)((total_steps + 2047) / 2048);
   int rc = ensure(h, h->tile_sum, ((size_t)n_tiles + 2) * sizeof(int));
   if (rc) return rc;
-  if (set_err(h, "launch_planes_count", launch_planes_count(B, h->P, step_off, inst_inter_legal, s))) return CSDO_ERR_CUDA;
+  if (set_err(h, "launch_planes_count", launch_planes_count(B, h->P, total_steps, step_off, inst_inter_legal, s))) return CSDO_ERR_CUDA;
   if (set_err(h, "launch_plane_offsets",
               launch_plane_offsets(B, total_steps, step_off, static_cast<int *>(h->tile_sum.p), plane_ptr, s)))
     return CSDO_ERR_CUDA;
@@ -479,7 +498,7 @@ int csdo_planes_count(csdo_handle *h, const csdo_batch *in, int32_t *plane_ptr, 
   csdo_batch dv = *in;
   dv.inst_agent_ptr = B.inst_agent_ptr; dv.inst_nt = B.inst_nt; dv.inst_dims = B.inst_dims; dv.obs_ptr = B.obs_ptr;
   dv.obs = B.obs; dv.agent_off = B.agent_off; dv.guess = B.guess; dv.plane_ptr = nullptr; dv.plane_t = nullptr;
-  dv.plane_abc = nullptr; dv.agent_order = nullptr;
+  dv.plane_abc = nullptr; dv.agent_order = nullptr; dv.n_active = 0;
   int64_t total = 0;
   if ((rc = csdo_planes_count_device(h, &dv, m.steps, d_off, d_ptr, d_legal, &total, h->stream))) return rc;
   if ((rc = download(h, plane_ptr, d_ptr, (size_t)in->n_agents + 1))) return rc;

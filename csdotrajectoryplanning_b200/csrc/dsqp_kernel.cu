@@ -1085,11 +1085,19 @@ __device__ __forceinline__ void refine_body(const DevBatch &B, const DevOut &O, 
       if (idx < ST.cap) {
         volatile int *slot = ST.items + idx;
         volatile int *remaining = queue + kQRemaining;
-        long long spins = 0;
+        // Liveness: a CTA only waits while the queue is empty and some SQP loop is still running; the CTAs
+        // that run those loops never wait for anybody, so they always reach their re-enqueue / retire step,
+        // which either fills this slot or drops `remaining` to 0.  That holds whether or not the whole grid
+        // is co-resident (a CTA that is not resident yet holds no slot).  The time bound below is a safety
+        // net against a lost update only: two minutes of wall clock, far beyond any refine.
+        unsigned long long t_start = 0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
         while ((a_next = *slot) < 0) {  // the slot is filled by the CTA that re-enqueues an agent
           if (*remaining <= 0) break;    // every SQP loop is finished: nothing will be appended any more
           __nanosleep(200);
-          if (++spins > 50000000LL) { atomicExch(queue + kQError, 1); break; }  // safety net, never expected
+          unsigned long long t_now;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));
+          if (t_now - t_start > 120000000000ull) { atomicExch(queue + kQError, 1); break; }
         }
       }
       s_agent = a_next;
@@ -1111,6 +1119,10 @@ __device__ __forceinline__ void refine_body(const DevBatch &B, const DevOut &O, 
     if (threadIdx.x == 0) {
       cs.Nt = Nt;
       cs.K = B.plane_ptr[a + 1] - B.plane_ptr[a];
+      if (cs.K > LY.KMAX) {  // the caller understated max_planes: stay inside the scratch slot and flag it (csdo_sync)
+        atomicExch(queue + kQError, 2);
+        cs.K = LY.KMAX;
+      }
       cs.pl = cs.K <= cs.KS ? cs.pl_smem : cs.pl_glob;
       cs.plane_t = B.plane_t + B.plane_ptr[a];
       cs.plane_abc = B.plane_abc + (size_t)12 * B.plane_ptr[a];
@@ -1352,10 +1364,11 @@ Layout make_layout(int NT, int KMAX, int tier, int KS, int PC) {
 }
 
 // queue and per-agent counters before the launch
-__global__ void queue_init_kernel(int n, const int *order, int *items, int cap, int *ctrl, int *sqp_iters) {
+__global__ void queue_init_kernel(int n, int n_agents, const int *order, int *items, int cap, int *ctrl,
+                                  int *sqp_iters) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < cap) items[i] = i < n ? (order ? order[i] : i) : -1;
-  if (i < n) sqp_iters[i] = 0;
+  if (i < n) sqp_iters[order ? order[i] : i] = 0;  // (an agent's first visit is recognised by sqp_iters == 0)
   if (i == 0) { ctrl[kQHead] = 0; ctrl[kQTail] = n; ctrl[kQRemaining] = n; ctrl[kQError] = 0; }
 }
 
@@ -1373,15 +1386,22 @@ cudaError_t launch_refine(const DevBatch &B, const DevOut &O, const csdo_params 
   if (e != cudaSuccess) return e;
   if (const char *co = getenv("CSDO_CARVEOUT"))  // developer knob: shared-memory carve-out in percent
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(co));
-  const int fb = 256, n = B.n_agents;
-  QueueState qs{static_cast<int *>(queue_items), (int)(refine_queue_bytes(n, P) / sizeof(int))};
+  const int fb = 256, n = (B.n_active > 0 && B.agent_order) ? B.n_active : B.n_agents;
+  QueueState qs{static_cast<int *>(queue_items), (int)(refine_queue_bytes(B.n_agents, P) / sizeof(int))};
   e = cudaMemsetAsync(queue, 0, 2048, stream);
   if (e != cudaSuccess) return e;
   fill_int_kernel<<<(B.n_inst + fb - 1) / fb, fb, 0, stream>>>(O.inst_static_legal, B.n_inst, 1);
-  queue_init_kernel<<<(qs.cap + fb - 1) / fb, fb, 0, stream>>>(n, B.agent_order, qs.items, qs.cap, queue, O.sqp_iters);
+  queue_init_kernel<<<(qs.cap + fb - 1) / fb, fb, 0, stream>>>(n, B.n_agents, B.agent_order, qs.items, qs.cap, queue,
+                                                               O.sqp_iters);
   kern<<<grid, block, smem, stream>>>(B, O, P, LY, scratch, queue, qs);
   aggregate_status_kernel<<<(B.n_inst + fb - 1) / fb, fb, 0, stream>>>(B, O);
   if (n_launches) *n_launches = 4;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_aggregate_status(const DevBatch &B, const DevOut &O, cudaStream_t stream) {
+  const int fb = 256;
+  aggregate_status_kernel<<<(B.n_inst + fb - 1) / fb, fb, 0, stream>>>(B, O);
   return cudaGetLastError();
 }
 

@@ -22,6 +22,7 @@ struct DevBatch {  // device pointers, same meaning as csdo_batch
   const int *plane_ptr, *plane_t;
   const double *plane_abc;
   const int *agent_order;  // may be null
+  int n_active;            // 0: all agents; else the first n_active entries of agent_order
 };
 
 struct DevOut {  // device pointers, same meaning as csdo_result
@@ -67,12 +68,13 @@ size_t refine_queue_bytes(int n_agents, const csdo_params &P);
 cudaError_t launch_refine(const DevBatch &B, const DevOut &O, const csdo_params &P, const Layout &LY,
                           double *scratch, int *queue, void *queue_items, int grid, int block, bool lean,
                           cudaStream_t stream, int *n_launches);
+cudaError_t launch_aggregate_status(const DevBatch &B, const DevOut &O, cudaStream_t stream);
 cudaError_t launch_corridors(const DevBatch &B, const csdo_params &P, int double_centres, double *corridors,
                              int *box_status, int *inst_static_legal, cudaStream_t stream);
 
 // neighbour pairs + planes (planes_kernel.cu)
-cudaError_t launch_planes_count(const DevBatch &B, const csdo_params &P, int *step_cnt, int *inst_inter_legal,
-                                cudaStream_t stream);
+cudaError_t launch_planes_count(const DevBatch &B, const csdo_params &P, int64_t total_steps, int *step_cnt,
+                                int *inst_inter_legal, cudaStream_t stream);
 cudaError_t launch_planes_fill(const DevBatch &B, const csdo_params &P, const int *step_off, int *plane_t,
                                double *plane_abc, int *plane_partner, cudaStream_t stream);
 cudaError_t launch_planes_from_pairs(const DevBatch &B, const csdo_params &P, int64_t n_pairs, const int *pairs,

@@ -104,7 +104,7 @@ __device__ __forceinline__ void pair_planes(const csdo_params &P, const DState &
 template <bool FILL>
 __global__ void planes_kernel(const DevBatch B, const csdo_params P, int *step_cnt, int *inst_inter_legal,
                               const int *step_off, int *plane_t, double *plane_abc, int *plane_partner) {
-  const int a = blockIdx.x;
+  const int a = (B.n_active > 0 && B.agent_order) ? B.agent_order[blockIdx.x] : (int)blockIdx.x;  // agent subset
   const int inst = find_instance(B, a);
   const int Nt = B.inst_nt[inst];
   const int a0 = B.inst_agent_ptr[inst], a1 = B.inst_agent_ptr[inst + 1];
@@ -144,18 +144,20 @@ __global__ void fill_int_kernel2(int *p, int n, int v) {
   if (i < n) p[i] = v;
 }
 
-cudaError_t launch_planes_count(const DevBatch &B, const csdo_params &P, int *step_cnt, int *inst_inter_legal,
-                                cudaStream_t stream) {
+cudaError_t launch_planes_count(const DevBatch &B, const csdo_params &P, int64_t total_steps, int *step_cnt,
+                                int *inst_inter_legal, cudaStream_t stream) {
   fill_int_kernel2<<<(B.n_inst + 255) / 256, 256, 0, stream>>>(inst_inter_legal, B.n_inst, 1);
+  const bool subset = B.n_active > 0 && B.agent_order;
+  if (subset) cudaMemsetAsync(step_cnt, 0, (size_t)total_steps * sizeof(int), stream);  // the other agents: no planes
   if (B.n_agents > 0)
-    planes_kernel<false><<<B.n_agents, 128, 0, stream>>>(B, P, step_cnt, inst_inter_legal, nullptr, nullptr, nullptr, nullptr);
+    planes_kernel<false><<<subset ? B.n_active : B.n_agents, 128, 0, stream>>>(B, P, step_cnt, inst_inter_legal, nullptr, nullptr, nullptr, nullptr);
   return cudaGetLastError();
 }
 
 cudaError_t launch_planes_fill(const DevBatch &B, const csdo_params &P, const int *step_off, int *plane_t,
                                double *plane_abc, int *plane_partner, cudaStream_t stream) {
   if (B.n_agents > 0)
-    planes_kernel<true><<<B.n_agents, 128, 0, stream>>>(B, P, nullptr, nullptr, step_off, plane_t, plane_abc,
+    planes_kernel<true><<<(B.n_active > 0 && B.agent_order) ? B.n_active : B.n_agents, 128, 0, stream>>>(B, P, nullptr, nullptr, step_off, plane_t, plane_abc,
                                                          plane_partner);
   return cudaGetLastError();
 }

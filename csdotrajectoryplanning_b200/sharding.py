@@ -148,3 +148,73 @@ def refine_agent_partitioned(batch: Batch, refine_fn: Callable[[Batch], RefineRe
     full.inst_static_legal[:] = legal
     aggregate_instance_status(batch, full)
     return full
+
+
+# ---------------------------------------------------------------------------------------------------
+# Device-resident agent partition (BASELINE configs[2]): every rank holds the WHOLE batch in HBM (the plane
+# build needs every agent's guess), marks its own agents active (csdo_batch.n_active), builds planes for
+# and refines only those, and ONE all-gather per step (NCCL on GPUs) gives every rank the whole solution.
+def rank_agent_ids(batch: Batch, rank: int, world: int) -> np.ndarray:
+    """Global ids of the agents rank `rank` owns: a contiguous slice of every instance's agents (all agents
+    of an instance share the horizon, so equal counts are equal work up to the plane counts)."""
+    ids: List[int] = []
+    for i in range(batch.n_inst):
+        a0, a1 = int(batch.inst_agent_ptr[i]), int(batch.inst_agent_ptr[i + 1])
+        na = a1 - a0
+        ids.extend(range(a0 + (na * rank) // world, a0 + (na * (rank + 1)) // world))
+    return np.asarray(ids, np.int32)
+
+
+class DeviceAllGather:
+    """Pack this rank's agents' results -> one all-gather (float64) + one (int32) -> unpack into the full-size
+    result tensors, all on the caller's stream; nothing touches the host.  Works on CUDA tensors with NCCL
+    and on CPU tensors with gloo (tests)."""
+
+    INT_FIELDS = ("status", "sqp_iters", "n_qp", "admm_iters", "n_factor")
+
+    def __init__(self, batch: Batch, rank: int, world: int, device, dist):
+        import torch
+        self.rank, self.world, self.dist, self.n_inst = rank, world, dist, batch.n_inst
+        off = batch.agent_off
+        self.ids, self.ti, self.ci = [], [], []
+        for r in range(world):
+            ids = rank_agent_ids(batch, r, world)
+            t = np.concatenate([np.arange(6 * off[a], 6 * off[a + 1]) for a in ids]) if ids.size else np.zeros(0, np.int64)
+            c = np.concatenate([np.arange(8 * off[a], 8 * off[a + 1]) for a in ids]) if ids.size else np.zeros(0, np.int64)
+            self.ids.append(torch.from_numpy(ids.astype(np.int64)).to(device))
+            self.ti.append(torch.from_numpy(t.astype(np.int64)).to(device))
+            self.ci.append(torch.from_numpy(c.astype(np.int64)).to(device))
+        self.flen = max(int(self.ti[r].numel() + self.ci[r].numel() + self.ids[r].numel()) for r in range(world))
+        self.ilen = max(int(len(self.INT_FIELDS) * self.ids[r].numel()) for r in range(world)) + batch.n_inst
+        self.fsend = torch.zeros(self.flen, dtype=torch.float64, device=device)
+        self.frecv = torch.zeros(world * self.flen, dtype=torch.float64, device=device)
+        self.isend = torch.zeros(self.ilen, dtype=torch.int32, device=device)
+        self.irecv = torch.zeros(world * self.ilen, dtype=torch.int32, device=device)
+        self.bytes_per_rank = 8 * self.flen + 4 * self.ilen
+
+    def run(self, t: dict) -> None:
+        """t: the DeviceResult tensor dict (full-size arrays); call inside the stream context of the refine."""
+        import torch
+        r = self.rank
+        nt, nc, na = self.ti[r].numel(), self.ci[r].numel(), self.ids[r].numel()
+        self.fsend[:nt] = t["traj"][self.ti[r]]
+        self.fsend[nt:nt + nc] = t["corridors"][self.ci[r]]
+        self.fsend[nt + nc:nt + nc + na] = t["objective"][self.ids[r]]
+        for j, k in enumerate(self.INT_FIELDS):
+            self.isend[j * na:(j + 1) * na] = t[k][self.ids[r]]
+        self.isend[self.ilen - self.n_inst:] = t["inst_static_legal"]
+        self.dist.all_gather(list(self.frecv.chunk(self.world)), self.fsend)
+        self.dist.all_gather(list(self.irecv.chunk(self.world)), self.isend)
+        legal = None
+        for q in range(self.world):
+            f, iv = self.frecv[q * self.flen:(q + 1) * self.flen], self.irecv[q * self.ilen:(q + 1) * self.ilen]
+            nt, nc, na = self.ti[q].numel(), self.ci[q].numel(), self.ids[q].numel()
+            if q != r:
+                t["traj"][self.ti[q]] = f[:nt]
+                t["corridors"][self.ci[q]] = f[nt:nt + nc]
+                t["objective"][self.ids[q]] = f[nt + nc:nt + nc + na]
+                for j, k in enumerate(self.INT_FIELDS):
+                    t[k][self.ids[q]] = iv[j * na:(j + 1) * na]
+            lg = iv[self.ilen - self.n_inst:]
+            legal = lg.clone() if legal is None else torch.minimum(legal, lg)
+        t["inst_static_legal"].copy_(legal)   # an instance is legal iff every rank's agents were

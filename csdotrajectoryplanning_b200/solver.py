@@ -67,6 +67,11 @@ class DsqpSolver:
                                                  dbatch.max_nt, dbatch.max_planes,
                                                  C.c_void_p(stream_ptr) if stream_ptr else None))
 
+    def aggregate_status_device(self, dbatch: "DeviceBatch", dres: "DeviceResult", stream_ptr: int = 0) -> None:
+        """SolverDSQP's status aggregation over all agents (after the all-gather of the agent-partitioned mode)."""
+        self._check(self._lib.csdo_aggregate_status_device(self._h, C.byref(dbatch.c), C.byref(dres.c),
+                                                           C.c_void_p(stream_ptr) if stream_ptr else None))
+
     def sync(self) -> None:
         """csdo_sync: waits for the last refine_device and raises if the device flagged an error."""
         self._check(self._lib.csdo_sync(self._h))
@@ -151,6 +156,15 @@ class DeviceBatch:
     def h2d_bytes(self) -> int:
         return int(sum(t.numel() * t.element_size() for t in self.t.values()))
 
+    def set_active(self, agent_ids: np.ndarray) -> None:
+        """Agent-partitioned mode: only these agents (global ids) get planes and are refined
+        (csdo_batch.agent_order + n_active)."""
+        import torch
+        self.active_ids = np.ascontiguousarray(agent_ids, np.int32)
+        self.t["agent_order"] = torch.from_numpy(self.active_ids).to(self.t["guess"].device)
+        self.c.agent_order = self.t["agent_order"].data_ptr()
+        self.c.n_active = int(self.active_ids.shape[0])
+
     def set_planes(self, plane_ptr, plane_t, plane_abc) -> None:
         """Attach device-resident planes (DsqpSolver.planes_device) and the processing order they imply."""
         import torch
@@ -159,7 +173,13 @@ class DeviceBatch:
         self.max_planes = int(k.max().item()) if k.numel() else 0
         nt = torch.from_numpy(self.host.agent_nt()).to(plane_ptr.device)
         cost = 13 * nt + 4 * k
-        self.t["agent_order"] = torch.argsort(-cost, stable=True).to(torch.int32)
+        active = getattr(self, "active_ids", None)
+        if active is None:
+            self.t["agent_order"] = torch.argsort(-cost, stable=True).to(torch.int32)
+        else:   # longest first among the rank's own agents
+            ids = torch.from_numpy(active.astype(np.int64)).to(plane_ptr.device)
+            self.t["agent_order"] = ids[torch.argsort(-cost[ids], stable=True)].to(torch.int32)
+            self.c.n_active = int(active.shape[0])
         for name in ("plane_ptr", "plane_t", "plane_abc", "agent_order"):
             ten = self.t[name]
             setattr(self.c, name, ten.data_ptr() if ten.numel() else None)

@@ -120,6 +120,14 @@ typedef struct csdo_batch {
                                     decides.  An agent is handed out for one SQP
                                     iteration at a time and re-enqueued until
                                     its loop ends. */
+  int32_t n_active;              /* 0 = every agent.  > 0 (needs agent_order):
+                                    only the first n_active agents of agent_order
+                                    are refined / get planes; the others' results
+                                    are left untouched and their plane lists are
+                                    empty.  This is the agent-partitioned multi-GPU
+                                    mode: every rank holds the whole batch (the
+                                    plane build needs every agent's guess) and
+                                    works on its own agents. */
 } csdo_batch;
 
 typedef struct csdo_result {
@@ -165,6 +173,13 @@ int csdo_refine(csdo_handle *h, const csdo_batch *in, csdo_result *out);
  * synchronizing. */
 int csdo_refine_device(csdo_handle *h, const csdo_batch *in, csdo_result *out,
                        int max_nt, int max_planes, void *cuda_stream);
+
+/* SolverDSQP's status aggregation (dsqp_solver.cc:1224-1243) over ALL agents of
+ * every instance from out->status into out->inst_status (DEVICE pointers).
+ * csdo_refine* run it themselves; it is exported for the agent-partitioned
+ * mode, where the statuses of the other ranks' agents arrive by all-gather. */
+int csdo_aggregate_status_device(csdo_handle *h, const csdo_batch *in,
+                                 csdo_result *out, void *cuda_stream);
 
 /* Waits for the last csdo_refine_device of this handle and reports what only
  * the device knows: CSDO_ERR_INVALID if an agent had more planes than the

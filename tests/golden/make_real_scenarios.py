@@ -1,0 +1,68 @@
+"""Mint tests/golden/real_scenarios.npz: REAL benchmark geometry of the reference (benchmark/*.yaml: map size,
+obstacles incl. the 2-element and dummy [-1,-1] forms, starts, goals) plus coarse plans for it from the
+stand-in prioritized planner (tools/coarse_planner.cpp, "f1-lite").  Needs /root/reference; the fixture
+travels to the GPU box.  Only instances the stand-in planner routes completely are kept (the reference's
+own PBS + Hybrid A* cannot be built offline).  Regenerate with:  python tests/golden/make_real_scenarios.py
+"""
+import glob
+import os
+import sys
+import time
+from concurrent.futures import ProcessPoolExecutor
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+REF = "/root/reference/benchmark"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+# (folder glob, instances tried per folder)
+FOLDERS = [("map50by50/agents5/*", 60), ("map50by50/agents10/*", 60), ("map50by50/agents15/*", 60),
+           ("map50by50/agents20/*", 60), ("map50by50/agents25/*", 60), ("room/agents10", 60), ("room/agents20", 60),
+           ("map100by100/agents25/*", 12), ("map100by100/agents100/empty", 2), ("map100by100/agents70/empty", 4)]
+
+
+def one(path):
+    from csdotrajectoryplanning_b200 import default_params
+    from csdotrajectoryplanning_b200.scenario import load_scenario_yaml
+    from tools import planner
+    p = default_params()
+    dx, dy, obs, st, gl = load_scenario_yaml(path)
+    t = time.time()
+    paths, nf = planner.plan(dx, dy, obs, st, gl, p, max_expansions=120000 if len(st) <= 25 else 40000)
+    return path, dx, dy, obs, st, gl, paths, nf, time.time() - t
+
+
+def main():
+    files = []
+    for pat, n in FOLDERS:
+        for d in sorted(glob.glob(os.path.join(REF, pat))):
+            files += sorted(glob.glob(os.path.join(d, "*.yaml")))[:n]
+    print(len(files), "scenario files")
+    out = dict(name=[], dims=[], obs_ptr=[0], obs=[], agent_ptr=[0], starts=[], goals=[], st_ptr=[0], states=[], actions=[])
+    tried = routed = 0
+    with ProcessPoolExecutor(8) as ex:
+        for path, dx, dy, obs, st, gl, paths, nf, dt in ex.map(one, files, chunksize=4):
+            tried += 1
+            if nf:
+                continue
+            routed += 1
+            out["name"].append(os.path.relpath(path, REF)); out["dims"].append([dx, dy])
+            out["obs"].append(obs.reshape(-1, 3)); out["obs_ptr"].append(out["obs_ptr"][-1] + obs.shape[0])
+            out["starts"].append(st); out["goals"].append(gl); out["agent_ptr"].append(out["agent_ptr"][-1] + len(st))
+            for s, a in paths:
+                out["states"].append(s); out["actions"].append(np.concatenate([a, [-1]]).astype(np.int8))
+                out["st_ptr"].append(out["st_ptr"][-1] + len(s))
+    print("routed completely:", routed, "of", tried)
+    np.savez_compressed(os.path.join(HERE, "real_scenarios.npz"),
+                        name=np.asarray(out["name"]), dims=np.asarray(out["dims"]), obs_ptr=np.asarray(out["obs_ptr"], np.int32),
+                        obs=np.concatenate(out["obs"]) if out["obs"] else np.zeros((0, 3)),
+                        agent_ptr=np.asarray(out["agent_ptr"], np.int32), starts=np.concatenate(out["starts"]),
+                        goals=np.concatenate(out["goals"]), st_ptr=np.asarray(out["st_ptr"], np.int32),
+                        states=np.concatenate(out["states"]).astype(np.float64), actions=np.concatenate(out["actions"]),
+                        tried=np.asarray([tried]), routed=np.asarray([routed]))
+
+
+if __name__ == "__main__":
+    main()

@@ -167,3 +167,62 @@ def test_gloo_world2_agent_partition(tmp_path, oracle):
     outs = [p.communicate(timeout=600)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"RANK {r} OK" in o, o[-2000:]
+
+
+_GLOO_GATHER_WORKER = r"""
+import os, sys
+import numpy as np
+import torch
+import torch.distributed as dist
+sys.path.insert(0, {root!r})
+sys.path.insert(0, os.path.join({root!r}, "tests"))
+from conftest import make_batch
+from csdotrajectoryplanning_b200 import default_params, sharding
+from csdotrajectoryplanning_b200.batch import RefineResult
+from oracle import oracle as O
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+p = default_params()
+b = make_batch(O, p, [21, 22, 23], na=7)          # 7 agents per instance: uneven split over 2 ranks
+whole = O.refine(p, b, linsys=1, nthreads=1)[0]   # the oracle stands in for the CUDA path on CPU
+ids = sharding.rank_agent_ids(b, rank, world)
+# what a rank holds after refining ONLY its own agents: everything else untouched (zeros / stale)
+t = {{k: torch.zeros_like(torch.from_numpy(np.ascontiguousarray(getattr(whole, k)))) for k in
+     ("traj", "corridors", "status", "sqp_iters", "n_qp", "admm_iters", "n_factor", "objective", "inst_status", "inst_static_legal")}}
+for a in ids:
+    o0, o1 = int(b.agent_off[a]), int(b.agent_off[a + 1])
+    t["traj"][6 * o0:6 * o1] = torch.from_numpy(whole.traj[6 * o0:6 * o1])
+    t["corridors"][8 * o0:8 * o1] = torch.from_numpy(whole.corridors[8 * o0:8 * o1])
+    for k in ("status", "sqp_iters", "n_qp", "admm_iters", "n_factor", "objective"):
+        t[k][a] = float(getattr(whole, k)[a]) if k == "objective" else int(getattr(whole, k)[a])
+t["inst_static_legal"][:] = 1
+if rank == 1: t["inst_static_legal"][0] = 0       # one rank saw an illegal start in instance 0
+g = sharding.DeviceAllGather(b, rank, world, torch.device("cpu"), dist)
+g.run(t)
+full = RefineResult.allocate(b)
+for k in ("traj", "corridors", "status", "sqp_iters", "n_qp", "admm_iters", "n_factor", "objective"):
+    getattr(full, k)[:] = t[k].numpy()
+sharding.aggregate_instance_status(b, full)
+ok = all(np.array_equal(getattr(full, k), getattr(whole, k)) for k in
+         ("traj", "corridors", "status", "sqp_iters", "n_qp", "admm_iters", "n_factor", "objective", "inst_status"))
+ok = ok and t["inst_static_legal"].tolist() == [0] + [1] * (b.n_inst - 1)
+covered = np.concatenate([sharding.rank_agent_ids(b, r, world) for r in range(world)])
+ok = ok and sorted(covered.tolist()) == list(range(b.n_agents))
+dist.barrier()
+print("RANK", rank, "OK" if ok else "MISMATCH", flush=True)
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)
+"""
+
+
+def test_gloo_world2_device_allgather(tmp_path, oracle):
+    """sharding.DeviceAllGather (the pack -> all-gather -> unpack of the agent-partitioned GPU mode) on CPU
+    tensors over gloo: every rank ends with the whole solution, the legality flag is AND-reduced."""
+    script = tmp_path / "worker_gather.py"
+    script.write_text(_GLOO_GATHER_WORKER.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29541", WORLD_SIZE="2", OMP_NUM_THREADS="1")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)),
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and f"RANK {r} OK" in o, o[-2000:]
