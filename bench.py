@@ -406,8 +406,8 @@ def main():
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         key = f"dram_bytes_per_agent_step_{args.workload}"
         if key in tj:       # ncu capture of a sub-batch of this workload, scaled by agent steps
-            traffic = tj[key] * float(batch.agent_nt().sum())
-            traffic_src = tj.get("source")
+            traffic = tj[key] * float(batch.agent_nt()[own].sum())
+            traffic_src = f'{tj.get("source")} (git {tj.get("git")}): ncu DRAM bytes per agent step x the agent steps of this launch'
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
@@ -485,7 +485,7 @@ def main():
             "refine_ms_per_instance": 1e3 * t_dev / args.steps / max(tot_inst, 1),   # whole job: step time / all instances
             "config": {"workload": workload_string(args.workload, total),
                        "instances_total": tot_inst, "agents_total": tot_agents, "qp_per_step_total": tot_qp // args.steps,
-                       "admm_iters_per_step_total": admm_tot, "planes_rank0": int(batch.plane_ptr[-1]),
+                       "admm_iters_per_step_total": admm_tot, "planes_rank0": int(batch.plane_ptr[-1]), "agent_steps_rank0": int(batch.agent_nt()[own].sum()),
                        "horizon_max": int(batch.inst_nt.max()), "l2": "256 MiB buffer written between timed iterations",
                        "parallelism": par, "launch": launch, "generation_s": t_gen},
             "clocks": clk, "gpu_launches": int(launch.get("launches", 0)) * args.steps,

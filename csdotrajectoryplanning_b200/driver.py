@@ -89,3 +89,33 @@ def run_mapset(instances: Sequence[Instance], solver, out_dir: Optional[str] = N
             dump_solutions(path, trajs, stat)
             rep.files.append(path)
     return rep
+
+
+def instances_from_coarse_plans(npz_path: str, params, select: Optional[Sequence[int]] = None) -> List[Instance]:
+    """Instances from a coarse-plan fixture (tests/golden/real_scenarios.npz: real benchmark geometry + coarse
+    (state, action) paths): InterpolateInitalGuess (scenario.interpolate_initial_guess, goals snapped as in
+    inter_agent_cons.cc:149-151) -> x0_bar, real map size and obstacles."""
+    from .scenario import interpolate_initial_guess
+    d = np.load(npz_path)
+    fast = None
+    try:      # the C++ header (include/csdo/initial_guess.h, bit-identical) when the tools library is built
+        from tools import synth
+        fast = synth.interpolate_paths
+    except Exception:
+        pass
+    out = []
+    for i in (range(len(d["name"])) if select is None else select):
+        a0, a1 = int(d["agent_ptr"][i]), int(d["agent_ptr"][i + 1])
+        if fast is not None:
+            s0, s1 = int(d["st_ptr"][a0]), int(d["st_ptr"][a1])
+            guess = fast(np.diff(d["st_ptr"][a0:a1 + 1]), d["states"][s0:s1], d["actions"][s0:s1], d["goals"][a0:a1], params)
+        else:
+            paths = []
+            for a in range(a0, a1):
+                s0, s1 = int(d["st_ptr"][a]), int(d["st_ptr"][a + 1])
+                paths.append((d["states"][s0:s1], d["actions"][s0:s1 - 1].astype(np.int32)))
+            guess = interpolate_initial_guess(paths, d["goals"][a0:a1], params)
+        o0, o1 = int(d["obs_ptr"][i]), int(d["obs_ptr"][i + 1])
+        out.append(Instance(guess=guess, dimx=float(d["dims"][i, 0]), dimy=float(d["dims"][i, 1]),
+                            obstacles=d["obs"][o0:o1].copy(), name=str(d["name"][i]).replace("/", "__")[:-5]))
+    return out

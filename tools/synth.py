@@ -32,6 +32,9 @@ def lib():
                                      C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
                                      C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.POINTER(C.c_int)]
         L.synth_instance.restype = C.c_int
+        L.interp_paths.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
+                                   C.c_double, C.c_int, C.c_void_p]
+        L.interp_paths.restype = C.c_int
         _lib = L
     return _lib
 
@@ -99,3 +102,18 @@ def workload_jobs(name: str, total: int, seed: int = 1234):
 # BASELINE.json configs[4]: 100x100 maps, 100 agents (the largest benchmark agent count), 50 obstacles,
 # horizons 127 / 190 / 256 (Nt in {128, 192, 256}; a horizon is 3 x coarse actions + 1)
 C5_SHAPES = [(100.0, 100, 50, (28, 42)), (100.0, 100, 50, (43, 63)), (100.0, 100, 50, (57, 85))]
+
+
+def interpolate_paths(n_states: np.ndarray, states: np.ndarray, actions: np.ndarray, goals, params) -> np.ndarray:
+    """include/csdo/initial_guess.h::InterpolateInitalGuess on flat arrays (bit-identical to
+    scenario.interpolate_initial_guess, which tests/test_initial_guess_cpp.py and tests/test_ref_pins.py pin)."""
+    ns = np.ascontiguousarray(n_states, np.int32)
+    st = np.ascontiguousarray(states, np.float64)
+    ac = np.ascontiguousarray(actions, np.int8)
+    gl = np.ascontiguousarray(goals, np.float64) if goals is not None else None
+    cap = int(3 * (ns.max() - 1) + 1)
+    out = np.zeros((ns.shape[0], 6, cap))
+    nt = lib().interp_paths(ns.shape[0], ns.ctypes.data, st.ctypes.data, ac.ctypes.data,
+                            gl.ctypes.data if gl is not None else None, params.dt, params.LF, params.LB, cap, out.ctypes.data)
+    assert nt > 0
+    return out[:, :, :nt].copy()

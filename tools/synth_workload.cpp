@@ -190,4 +190,34 @@ int synth_instance(uint64_t seed, double size, int n_agents, int n_obs, int act_
   return 0;
 }
 
+// InterpolateInitalGuess (include/csdo/initial_guess.h) for Na coarse paths given as flat arrays: states
+// [sum n_states][3], actions [sum n_states] (one unused slot per agent at its end), goals [Na][3] or NULL.
+// out: Na x 6 planes of nt_cap; returns the horizon or -1.
+int interp_paths(int Na, const int *n_states, const double *states, const signed char *actions, const double *goals,
+                 double dt, double LF, double LB, int nt_cap, double *out) {
+  using namespace libMultiRobotPlanning;
+  std::vector<CoarsePath> paths(Na);
+  std::vector<CoarseState> gl(Na);
+  size_t so = 0;
+  for (int a = 0; a < Na; ++a) {
+    for (int i = 0; i < n_states[a]; ++i, ++so) {
+      paths[a].states.push_back(CoarseState{states[3 * so], states[3 * so + 1], states[3 * so + 2]});
+      if (i + 1 < n_states[a]) paths[a].actions.push_back((int)actions[so]);
+    }
+    if (goals) gl[a] = CoarseState{goals[3 * a], goals[3 * a + 1], goals[3 * a + 2]};
+  }
+  std::vector<std::vector<OptimizeResult>> x0;
+  InterpolateInitalGuess(paths, x0, goals ? &gl : nullptr, dt, LF, LB);
+  const int nt = (int)x0[0].size();
+  if (nt > nt_cap) return -1;
+  for (int a = 0; a < Na; ++a)
+    for (int t = 0; t < nt; ++t) {
+      const OptimizeResult &r = x0[a][t];
+      double *p = out + (size_t)a * 6 * nt_cap;
+      p[t] = r.x; p[nt_cap + t] = r.y; p[2 * nt_cap + t] = r.yaw; p[3 * nt_cap + t] = r.steer; p[4 * nt_cap + t] = r.v;
+      p[5 * nt_cap + t] = r.d_steer;
+    }
+  return nt;
+}
+
 }  // extern "C"
