@@ -157,6 +157,14 @@ def cpu_sample(p, inst, target_core_s: float, nthreads: int):
     return pack_instances(with_oracle_planes(p, [inst[i] for i in chosen])), chosen
 
 
+def config_dict(args, total: int) -> dict:
+    """The `config` object, identical in both arms (the driver compares them): what a step is."""
+    return {"workload": workload_string(args.workload, total), "instances_per_step": total,
+            "partition": args.partition,
+            "l2": "b200 arm: 256 MiB buffer written between timed iterations (outside the events); "
+                  "reference arm: host cores, no GPU"}
+
+
 def run_reference(args, rank: int, world: int):
     if rank != 0:
         return
@@ -181,7 +189,7 @@ def run_reference(args, rank: int, world: int):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "refine_ms_per_instance": 1e3 * t_tot / args.steps / len(chosen),
-            "config": {"workload": workload_string(args.workload, total), "sample": desc},
+            "config": config_dict(args, total), "details": {"sample": desc},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
@@ -483,11 +491,11 @@ def main():
             "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "refine_ms_per_instance": 1e3 * t_dev / args.steps / max(tot_inst, 1),   # whole job: step time / all instances
-            "config": {"workload": workload_string(args.workload, total),
-                       "instances_total": tot_inst, "agents_total": tot_agents, "qp_per_step_total": tot_qp // args.steps,
-                       "admm_iters_per_step_total": admm_tot, "planes_rank0": int(batch.plane_ptr[-1]), "agent_steps_rank0": int(batch.agent_nt()[own].sum()),
-                       "horizon_max": int(batch.inst_nt.max()), "l2": "256 MiB buffer written between timed iterations",
-                       "parallelism": par, "launch": launch, "generation_s": t_gen},
+            "config": config_dict(args, total),
+            "details": {"instances_total": tot_inst, "agents_total": tot_agents, "qp_per_step_total": tot_qp // args.steps,
+                        "admm_iters_per_step_total": admm_tot, "planes_rank0": int(batch.plane_ptr[-1]),
+                        "agent_steps_rank0": int(batch.agent_nt()[own].sum()), "horizon_max": int(batch.inst_nt.max()),
+                        "parallelism": par, "launch": launch, "generation_s": t_gen},
             "clocks": clk, "gpu_launches": int(launch.get("launches", 0)) * args.steps,
             "e2e": {"value": tot_qp / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * t_e2e / args.steps, "steps_timed": e2e_steps, "matches_device_arm": e2e_ok,

@@ -198,7 +198,7 @@ int run_refine(csdo_handle *h, const DevBatch &B, const DevOut &O, int max_nt, i
   for (int tier = 0; tier <= 3; ++tier) {
     if (force && tier != atoi(force)) continue;
     if (!force && tier >= 2 && occ > 0) break;
-    const Layout l = make_layout(NT, KMAX, tier, 0, 0);
+    const Layout l = make_layout(NT, KMAX, tier, 0, 0, false);
     if (l.smem_doubles * 8 + 1024 > h->smem_limit) continue;
     const char *no_lean = getenv("CSDO_NO_LEAN");  // developer knob: never use the register-lean kernel variants
     for (int ln = 0; ln < ((no_lean && atoi(no_lean)) ? 1 : 2); ++ln) {
@@ -210,13 +210,23 @@ int run_refine(csdo_handle *h, const DevBatch &B, const DevOut &O, int max_nt, i
     // spend the shared memory that the chosen residency leaves free on (1) the per-plane contribution
     // buffer of the plane-major passes (3 doubles per plane in the ADMM loop), (2) the agents' plane rows
     // (192 B per plane): agents with K <= KS keep them on chip, the rest use global scratch
-    int budget = (h->smem_limit_sm / occ - 1024 - LY.smem_doubles * 8) / 8;  // doubles
-    budget = std::max(0, budget - 8);
-    const int PC = std::min(3 * KMAX, budget) & ~1;
+    // (a block may use sharedMemPerBlockOptin at most, which is 1 KB less than the SM's capacity)
+    int budget = (std::min(h->smem_limit_sm / occ - 1024, h->smem_limit - 600) - LY.smem_doubles * 8) / 8;  // doubles
+    budget = std::max(0, budget - 16);
+    // Measured (B200, Nt = 256, 1 CTA/SM): spending the ~37 KB that are left on w or on plane records is no
+    // faster than leaving them to L1 (the row data then hits L1 instead) -- 44.3 k vs 45.3 k QP/s -- so the
+    // extras are only used on request
+    if (!getenv("CSDO_EXTRA_SMEM")) budget = 0;
+    // (0) tier 1: the fixed rows' state w (16 NT doubles, read and written in every pass) back on chip
+    const bool w_smem = (LY.tier & 1) && budget >= 16 * NT && !getenv("CSDO_NO_W_SMEM");
+    if (w_smem) budget -= 16 * NT;
+    // (1) contribution buffer for agents whose planes do not fit the solve scratch (3 K > 6 NT)
+    const int PC = (3 * KMAX > 6 * NT) ? (std::min(3 * KMAX, budget) & ~1) : 0;
     int KS = std::min(KMAX, std::max(0, (budget - PC) / (PL_BYTES_PER_PLANE / 8)));
     KS &= ~1;
-    Layout l = make_layout(NT, KMAX, LY.tier, KS, PC);
+    Layout l = make_layout(NT, KMAX, LY.tier, KS, PC, w_smem);
     if (refine_occupancy(block, l.smem_doubles * 8, lean) >= occ) LY = l;
+    else if (getenv("CSDO_PROFILE")) fprintf(stderr, "[csdo] extra shared-memory layout rejected (%d B)\n", l.smem_doubles * 8);
   }
   if (occ < 1) { h->err = "horizon does not fit the kernel's shared-memory layout"; return CSDO_ERR_UNSUPPORTED; }
   if (const char *cap = getenv("CSDO_MAX_CTAS_PER_SM")) occ = std::max(1, std::min(occ, atoi(cap)));  // developer knob

@@ -53,7 +53,7 @@ enum Var : int { VX = 0, VY, VP, VS, VV, VW, NX, NY, NP, NS };
 // between barriers): keeping two dozen pointers per thread in registers starved the row passes.
 struct CtxShared {
   int Nt, NT, K, KP, No, KS;
-  bool l_shared, rows_glob;
+  bool l_shared, rows_glob, w_shared;
   // shared-memory vectors, SoA with stride NT: v[k*NT + t]
   double *x, *xt, *rhs, *D, *carry, *red;
   int *pstart;   // [Nt+1] first plane of each step
@@ -64,6 +64,7 @@ struct CtxShared {
   PbcrMem pm;    // reduced-KKT factor storage (pbcr_solver.cuh)
   csdo_params P; // copy of the parameters for the out-of-line (cold) phases
   void *fn_solve; // band solve entry point (indirect call, see dsqp_kernel.cu)
+  void *fn_sweep; // the sweeps alone (developer variants)
   // per-CTA global scratch
   double *cur, *sol, *dy;
   double *pl;    // plane rows of this agent: shared memory when they fit (K <= KS), else global scratch
@@ -88,7 +89,7 @@ struct Ctx {
 #endif
 #define CSDO_GET(type, name) __device__ __forceinline__ type name() const { return s->name; }
   CSDO_GET(int, Nt) CSDO_GET(int, NT) CSDO_GET(int, K) CSDO_GET(int, KP) CSDO_GET(int, No) CSDO_GET(int, KS)
-  CSDO_GET(bool, l_shared) CSDO_GET(bool, rows_glob)
+  CSDO_GET(bool, l_shared) CSDO_GET(bool, rows_glob) CSDO_GET(bool, w_shared)
   CSDO_GET(double *, x) CSDO_GET(double *, xt) CSDO_GET(double *, rhs) CSDO_GET(double *, D)
   CSDO_GET(double *, carry) CSDO_GET(double *, red) CSDO_GET(int *, pstart) CSDO_GET(double *, ros)
   CSDO_GET(double *, cfgs) CSDO_GET(double *, Es) CSDO_GET(double *, ws)
@@ -166,7 +167,15 @@ __device__ __forceinline__ void rows_load(const Ctx &c, RowRegs &R) {
 #pragma unroll
     for (int i = 0; i < RO_COUNT; ++i) R.ro[i] = ro_[i * NTs];
 #pragma unroll
-    for (int i = 0; i < 13; ++i) { R.E[i] = Ep[i * NTs]; R.w[i] = wp[i * NTs]; }
+    for (int i = 0; i < 13; ++i) R.E[i] = Ep[i * NTs];
+    if (c.w_shared()) {   // the state w alone is back in shared memory
+      __builtin_assume(__isShared(wp));
+#pragma unroll
+      for (int i = 0; i < 13; ++i) R.w[i] = wp[i * NTs];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 13; ++i) R.w[i] = wp[i * NTs];
+    }
   } else {
     __builtin_assume(__isShared(ro_)); __builtin_assume(__isShared(Ep)); __builtin_assume(__isShared(wp));
 #pragma unroll
@@ -181,11 +190,17 @@ __device__ __forceinline__ void rows_store(const Ctx &c, const RowRegs &R) {
   const int t = c.t(), NTs = c.NT();
   double *Ep = c.Es() + t, *wp = c.ws() + t;
   if (c.rows_glob()) {
+    if (WRITE_W && c.w_shared()) {
+      __builtin_assume(__isShared(wp));
 #pragma unroll
-    for (int i = 0; i < 13; ++i) {
-      if (WRITE_W) wp[i * NTs] = R.w[i];
-      if (WRITE_E) Ep[i * NTs] = R.E[i];
+      for (int i = 0; i < 13; ++i) wp[i * NTs] = R.w[i];
+    } else if (WRITE_W) {
+#pragma unroll
+      for (int i = 0; i < 13; ++i) wp[i * NTs] = R.w[i];
     }
+#pragma unroll
+    for (int i = 0; i < 13; ++i)
+      if (WRITE_E) Ep[i * NTs] = R.E[i];
   } else {
     __builtin_assume(__isShared(Ep)); __builtin_assume(__isShared(wp));
 #pragma unroll
@@ -261,7 +276,9 @@ __device__ __forceinline__ void visit_planes(Ctx &c, const csdo_params &P, F &f)
   if (K == 0) return;  // CTA-uniform
   const int NT = c.NT();
   constexpr int NOUT = F::kPlaneOut;
-  double *pc = (NOUT * K <= c.pc_cap()) ? c.pc_smem() : c.pc_glob();
+  // contribution buffer: the solve scratch xt (6 NT doubles, idle in every pass that does not read the iterate
+  // from it), else the dedicated shared-memory buffer, else global scratch
+  double *pc = (IN != IN_XT && NOUT * K <= 6 * NT) ? c.xt() : ((NOUT * K <= c.pc_cap()) ? c.pc_smem() : c.pc_glob());
   const bool on_chip = c.pl() == c.pl_smem();
   for (int k = c.tid(); k < K; k += c.nthr()) {
     double2 *q2 = reinterpret_cast<double2 *>(c.pl() + (size_t)PL_COUNT * 4 * k);

@@ -847,21 +847,35 @@ __device__ __noinline__ int termination_status_cold(CtxShared *s, double cc, con
   return termination_status(c, s->P, *co, approximate);
 }
 
-// the band solve as its own function: its register allocation (the sweeps want ~200 registers) is then
-// independent of what the ADMM loop keeps live
+// The band solve as its own function.  Its sweeps want ~200 registers; a noinline function called directly is
+// capped by what is live in its caller (1.1 KB of spills inside the sweeps), while a call through a function
+// pointer read from device memory follows the full ABI and gives the callee the whole register file.  Which
+// part goes behind the pointer depends on the register class, see the body.  Tried as well
+// (-DCSDO_SWEEP_ONLY_INDIRECT): the sweeps behind the pointer and the rest of the solve inline in the ADMM
+// loop -- 2-4 % slower on every workload.
 template <int RC>
 __device__ __noinline__ void band_solve_call(CtxShared *s) {
   __builtin_assume(__isShared(s));
   const PbcrMem pm = s->pm;
-  if (s->l_shared) pbcr_solve_cta<true>(pm, s->rhs, s->xt, s->Nt, s->NT);
-  else pbcr_solve_cta<false>(pm, s->rhs, s->xt, s->Nt, s->NT);
+  if (RC == 0) {
+    // 255-register variants: this function is called DIRECTLY and stays light (separator phases only); the two
+    // 3-block sweeps, which want ~200 registers, go through a pointer and only the Nt/4 threads that own a
+    // partition pay the callee-saved save/restore (measured +5 % at Nt >= 128 against the whole solve behind
+    // the pointer, where all 256 threads push 110 KB of registers through L2 per solve)
+    if (s->l_shared) pbcr_solve_cta<true, true>(pm, s->rhs, s->xt, s->Nt, s->NT, s->fn_sweep);
+    else pbcr_solve_cta<false, true>(pm, s->rhs, s->xt, s->Nt, s->NT, s->fn_sweep);
+  } else {
+    // 168- / 128-register variants: the whole solve behind the pointer (measured 5 % faster at Nt <= 96, 3 CTAs/SM)
+    if (s->l_shared) pbcr_solve_cta<true>(pm, s->rhs, s->xt, s->Nt, s->NT);
+    else pbcr_solve_cta<false>(pm, s->rhs, s->xt, s->Nt, s->NT);
+  }
 }
+using BandSolveFn = void (*)(CtxShared *);
+__device__ BandSolveFn g_band_solve[3] = {band_solve_call<0>, band_solve_call<1>, band_solve_call<2>};
+__device__ PbcrSweepFn g_pbcr_sweep[2] = {pbcr_sweep_entry<false>, pbcr_sweep_entry<true>};
 
 // solveOSQP (dsqp_solver.cc:423-555): setup + warm start + ADMM; solution in c.sol()
 
-
-using BandSolveFn = void (*)(CtxShared *);
-__device__ BandSolveFn g_band_solve[3] = {band_solve_call<0>, band_solve_call<1>, band_solve_call<2>};
 
 // RC: register class of the kernel variant (0: 255, 1: 168, 2: 128 registers).  The out-of-line phases are
 // instantiated per class: a function shared by all variants would be compiled for the smallest budget.
@@ -893,15 +907,25 @@ __device__ __forceinline__ QpOut solve_qp(Ctx &c, const csdo_params &P, const La
   int iter = 0;
   PH_ADD(5);
   for (iter = 1; iter <= P.osqp_max_iter; ++iter) {
-    // entered through a function pointer read from device memory: an indirect call follows the full ABI, so
-    // the callee may use the whole register file (a direct call leaves it only the registers that are
-    // not live in the caller)
-    reinterpret_cast<BandSolveFn>(c.s->fn_solve)(c.s);
+#ifdef CSDO_SWEEP_ONLY_INDIRECT
+    {
+      const PbcrMem pm = c.s->pm;
+      if (c.l_shared()) pbcr_solve_cta<true, true>(pm, c.rhs(), c.xt(), Nt, NT, c.s->fn_solve);
+      else pbcr_solve_cta<false, true>(pm, c.rhs(), c.xt(), Nt, NT, c.s->fn_solve);
+    }
+#else
+    if (RC == 0) band_solve_call<RC>(c.s);
+    else reinterpret_cast<BandSolveFn>(c.s->fn_solve)(c.s);
+#endif
     PH_ADD(4);
     const bool can_check = P.check_termination && (iter % P.check_termination == 0);
     const bool store_dy = keep_dy && (can_check || iter == P.osqp_max_iter);
     if (iter == 1) step_rows_cold<RC, 1, true>(c.s, c.rho, c.c, store_dy, 0.0);
+#ifdef CSDO_ROWS_INLINE   // (developer switch: the hot row pass inline measured 2-3 % slower than out of line)
+    else step_rows<2, true>(c, P, store_dy, 0.0);
+#else
     else step_rows_cold<RC, 2, true>(c.s, c.rho, c.c, store_dy, 0.0);
+#endif
     PH_ADD(5);
     checked = false;
     const bool adapt = P.adaptive_rho && P.adaptive_rho_interval && (iter % P.adaptive_rho_interval == 0);
@@ -1053,7 +1077,12 @@ __device__ __forceinline__ void refine_body(const DevBatch &B, const DevOut &O, 
   if (threadIdx.x == 0) {
     cs.NT = LY.NT; cs.KP = 4 * LY.KMAX;
     cs.P = P;
+#ifdef CSDO_SWEEP_ONLY_INDIRECT
+    cs.fn_solve = reinterpret_cast<void *>(*(volatile PbcrSweepFn *)&g_pbcr_sweep[(LY.tier & 2) ? 0 : 1]);
+#else
     cs.fn_solve = reinterpret_cast<void *>(*(volatile BandSolveFn *)&g_band_solve[RC]);
+#endif
+    cs.fn_sweep = reinterpret_cast<void *>(*(volatile PbcrSweepFn *)&g_pbcr_sweep[(LY.tier & 2) ? 0 : 1]);
     cs.x = smem + LY.o_x; cs.xt = smem + LY.o_xt; cs.rhs = smem + LY.o_rhs; cs.D = smem + LY.o_D;
     cs.carry = smem + LY.o_carry; cs.red = smem + LY.o_red;
     const bool rows_glob = LY.tier & 1;
@@ -1061,7 +1090,8 @@ __device__ __forceinline__ void refine_body(const DevBatch &B, const DevOut &O, 
     cs.ros = rows_glob ? slot + LY.g_ro : smem + LY.o_ro;
     cs.cfgs = cs.ros + RO_COUNT * NT;
     cs.Es = rows_glob ? slot + LY.g_E : smem + LY.o_E;
-    cs.ws = rows_glob ? slot + LY.g_w : smem + LY.o_w;
+    cs.ws = (rows_glob && !LY.w_smem) ? slot + LY.g_w : smem + LY.o_w;
+    cs.w_shared = !rows_glob || LY.w_smem;
     cs.pstart = reinterpret_cast<int *>(smem + LY.o_pstart);
     cs.pm.L = (LY.tier & 2) ? slot + LY.g_L : smem + LY.o_L;
     cs.l_shared = !(LY.tier & 2);
@@ -1256,7 +1286,9 @@ template <int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
 dsqp_refine_kernel(const DevBatch B, const DevOut O, const csdo_params P, const Layout LY, double *scratch,
                    int *queue, const QueueState ST) {
-  refine_body<(MAXT == 512) ? 2 : (((MAXT == 96 && MINB == 3) || (MAXT == 160 && MINB == 2)) ? 1 : 0)>(B, O, P, LY, scratch, queue, ST);
+  // register class: 0 = 255 registers, 1 = 168 (three warps per sub-partition), 2 = 128 (four)
+  constexpr int kWarps = MAXT / 32 * MINB;
+  refine_body<(kWarps > 12) ? 2 : ((kWarps > 8) ? 1 : 0)>(B, O, P, LY, scratch, queue, ST);
 }
 
 using RefineKernel = void (*)(const DevBatch, const DevOut, const csdo_params, const Layout, double *, int *,
@@ -1275,6 +1307,8 @@ static RefineKernel pick_kernel(int block, bool lean) {
   if (block <= 96) return lean ? dsqp_refine_kernel<96, 3> : dsqp_refine_kernel<96, 2>;
   if (block <= 128) return dsqp_refine_kernel<128, 2>;
   if (block <= 160 && lean) return dsqp_refine_kernel<160, 2>;
+  if (block <= 192 && lean) return dsqp_refine_kernel<192, 2>;
+  if (block <= 256 && lean) return dsqp_refine_kernel<256, 2>;
   if (block <= 256) return dsqp_refine_kernel<256, 1>;
   return dsqp_refine_kernel<512, 1>;
 #endif
@@ -1330,11 +1364,11 @@ __global__ void corridors_kernel(const DevBatch B, const csdo_params P, int doub
 // ===================================================================
 // host-side launchers (called from csdo_api.cpp through dsqp_launch.h)
 // ===================================================================
-Layout make_layout(int NT, int KMAX, int tier, int KS, int PC) {
+Layout make_layout(int NT, int KMAX, int tier, int KS, int PC, bool w_smem) {
   // tier bit 0: per-step row data / row scaling / row state in global scratch instead of shared memory
   // tier bit 1: band factor in global scratch
   Layout l{};
-  l.NT = NT; l.KMAX = KMAX; l.tier = tier; l.KS = KS; l.PC = PC;
+  l.NT = NT; l.KMAX = KMAX; l.tier = tier; l.KS = KS; l.PC = PC; l.w_smem = (tier & 1) && w_smem;
   const bool rows_glob = tier & 1, band_glob = tier & 2;
   int o = 0;
   auto take = [&](int n) { int r = o; o += (n + 1) & ~1; return r; };
@@ -1351,6 +1385,7 @@ Layout make_layout(int NT, int KMAX, int tier, int KS, int PC) {
   l.o_L = band_glob ? 0 : take(pbcr_L_doubles(NT));
   l.o_pl = take(PL_COUNT * 4 * KS);
   l.o_pc = take(PC);
+  if (l.w_smem) l.o_w = take(16 * NT);  // tier 1 with room left: the rows' ADMM state w back on chip (read + written every pass)
   l.smem_doubles = o;
   size_t g = 0;
   auto gtake = [&](size_t n) { size_t r = g; g += (n + 1) & ~(size_t)1; return r; };

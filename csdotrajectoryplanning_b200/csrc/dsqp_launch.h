@@ -54,11 +54,12 @@ struct Layout {
   int NT, KMAX, tier, smem_doubles;
   int KS;  // planes per agent that fit the shared-memory plane area
   int PC;  // doubles of the shared-memory plane-contribution buffer (visit_planes)
+  bool w_smem;  // tier 1 only: the fixed rows' state w kept in shared memory
   int o_x, o_xt, o_rhs, o_D, o_carry, o_red, o_pstart, o_L, o_sinv, o_pl, o_pc, o_ro, o_E, o_w;
   size_t g_cur, g_sol, g_dy, g_pl, g_pc, g_L, g_ro, g_E, g_w, slot_doubles;
 };
 
-Layout make_layout(int NT, int KMAX, int tier, int KS, int PC);
+Layout make_layout(int NT, int KMAX, int tier, int KS, int PC, bool w_smem);
 int refine_occupancy(int block, int smem_bytes, bool lean);
 int refine_kernel_regs(int block, bool lean);
 void read_debug_counters(unsigned long long *out16);

@@ -555,8 +555,11 @@ CSDO_HD void pbcr_bcr_backward_task(const PbcrMem &m, const PGeom &g, int s, int
 
 // S4 for partition p: b of the last interior block -= H[sep][last]' x_sep, then the sweeps with the
 // previous separator's solution riding on the forward sweep.  b is overwritten by x.
-template <bool SH>
-CSDO_HD void pbcr_final_partition(const PbcrMem &m, const PGeom &g, double *b, int NT, int p) {
+// the sweeps through a function pointer (device only, see pbcr_solve_cta): same arguments as pbcr_interior_solve
+using PbcrSweepFn = void (*)(const double *, int, const double *, double *, int, int, const double *);
+
+template <bool SH, bool INDIRECT = false>
+CSDO_HD void pbcr_final_partition(const PbcrMem &m, const PGeom &g, double *b, int NT, int p, void *sweep_fn = nullptr) {
   const double *P = m.L + p * kGrpD;
   const int len = g.part_len(p), t0 = kPM * p;
   if (p < g.Ps) {
@@ -571,7 +574,8 @@ CSDO_HD void pbcr_final_partition(const PbcrMem &m, const PGeom &g, double *b, i
       b[kc * NT + tl] = a;
     }
   }
-  pbcr_interior_solve<SH>(P, len, b, b, t0, NT, p > 0 ? m.xs + 6 * (p - 1) : nullptr);
+  if (INDIRECT) reinterpret_cast<PbcrSweepFn>(sweep_fn)(P, len, b, b, t0, NT, p > 0 ? m.xs + 6 * (p - 1) : nullptr);
+  else pbcr_interior_solve<SH>(P, len, b, b, t0, NT, p > 0 ? m.xs + 6 * (p - 1) : nullptr);
 }
 
 #if defined(__CUDACC__)
@@ -602,20 +606,39 @@ __device__ __forceinline__ void pbcr_factor_cta(const PbcrMem &m, int Nt) {
 // pointers then live in registers (a reference to the shared context made every access a dependent pair of
 // loads, re-done after every barrier).  The last BCR levels (at most 10 active separators = 60 row tasks)
 // are run by warp 0 alone between warp-level barriers.
+// sweep_fn (optional): entry point of an out-of-line copy of pbcr_interior_solve<SH>.  Only the threads that
+// own a partition run the sweeps, and only the sweeps want ~200 registers: called through a pointer they get a
+// register allocation of their own (full ABI), while the rest of the solve stays in the caller's.
 template <bool SH>
-__device__ __forceinline__ void pbcr_solve_cta(const PbcrMem m, double *b, double *tmp, int Nt, int NT) {
+__device__ __noinline__ void pbcr_sweep_entry(const double *P, int len, const double *in, double *out, int t0, int NT,
+                                              const double *prev_init) {
+  if (SH) { __builtin_assume(__isShared(P)); }
+  __builtin_assume(__isShared(in)); __builtin_assume(__isShared(out));
+  if (prev_init) __builtin_assume(__isShared(prev_init));
+  pbcr_interior_solve<SH>(P, len, in, out, t0, NT, prev_init);
+}
+
+template <bool SH, bool INDIRECT = false>
+__device__ __forceinline__ void pbcr_solve_cta(const PbcrMem m, double *b, double *tmp, int Nt, int NT,
+                                               void *sweep_fn = nullptr) {
   if (SH) __builtin_assume(__isShared(m.L));
   __builtin_assume(__isShared(m.S)); __builtin_assume(__isShared(m.g)); __builtin_assume(__isShared(m.y));
   __builtin_assume(__isShared(m.xs)); __builtin_assume(__isShared(b)); __builtin_assume(__isShared(tmp));
   const PGeom g = pbcr_geom(Nt);
   const int tid = threadIdx.x, nth = blockDim.x;
   if (g.Ps == 0) {
-    if (tid == 0) pbcr_interior_solve<SH>(m.L, g.part_len(0), b, b, 0, NT, nullptr);
+    if (tid == 0) {
+      if (INDIRECT) reinterpret_cast<PbcrSweepFn>(sweep_fn)(m.L, g.part_len(0), b, b, 0, NT, nullptr);
+      else pbcr_interior_solve<SH>(m.L, g.part_len(0), b, b, 0, NT, nullptr);
+    }
     __syncthreads();
     return;
   }
   DBG_INIT();
-  if (tid < g.NP) pbcr_interior_solve<SH>(m.L + tid * kGrpD, g.part_len(tid), b, tmp, kPM * tid, NT, nullptr);
+  if (tid < g.NP) {
+    if (INDIRECT) reinterpret_cast<PbcrSweepFn>(sweep_fn)(m.L + tid * kGrpD, g.part_len(tid), b, tmp, kPM * tid, NT, nullptr);
+    else pbcr_interior_solve<SH>(m.L + tid * kGrpD, g.part_len(tid), b, tmp, kPM * tid, NT, nullptr);
+  }
   DBG_ACC(0);   // S1 sweeps (thread 0 takes part)
   __syncthreads();
   DBG_ACC(1);   // barrier after S1
@@ -650,7 +673,7 @@ __device__ __forceinline__ void pbcr_solve_cta(const PbcrMem m, double *b, doubl
     __syncthreads();
   }
   DBG_ACC(3);   // BCR forward + backward levels
-  if (tid < g.NP) pbcr_final_partition<SH>(m, g, b, NT, tid);
+  if (tid < g.NP) pbcr_final_partition<SH, INDIRECT>(m, g, b, NT, tid, sweep_fn);
   DBG_ACC(4);   // S4 sweeps
   for (int task = tid; task < 6 * g.Ps; task += nth) b[(task % 6) * NT + g.sep_block(task / 6)] = m.xs[task];
   __syncthreads();

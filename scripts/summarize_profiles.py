@@ -39,7 +39,7 @@ summ = {a: (c, b) for a, b, c in zip(rr[0], rr[1], rr[2]) if a in want}
 mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 tr = sum(float(summ[k][0].replace(",", "")) * mult[summ[k][1]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
 line = [l for l in open(f"gpurun_out/{tag}_bench_under_ncu.log") if l.startswith("{")][-1]
-steps = json.loads(line)["config"]["agent_steps_rank0"]
+steps = json.loads(line)["details"]["agent_steps_rank0"]
 git = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
 tj = {}
 if os.path.exists("profiles/traffic.json"):
