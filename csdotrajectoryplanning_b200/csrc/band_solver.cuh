@@ -35,18 +35,10 @@
 
 namespace csdo {
 
-// developer counters: cycle timers of the factor / solve parts, compiled in with -DCSDO_DEV_TIMERS
-// (make DEV=-DCSDO_DEV_TIMERS) and printed by csdo_refine when CSDO_PROFILE is set
-__device__ unsigned long long g_dbg[16];
-#ifdef CSDO_DEV_TIMERS
-#define DBG_T(i) do { if (lane == 0) { long long t_ = clock64(); atomicAdd(&g_dbg[i], (unsigned long long)(t_ - dbg_t0)); dbg_t0 = t_; } } while (0)
-#define DBG_TB(i) do { if (lane == 0) { long long t_ = clock64(); atomicAdd(&g_dbg[i], (unsigned long long)(t_ - dbg_t0b)); dbg_t0b = t_; } } while (0)
-#define DBG_CLOCK() clock64()
-#else
+// (the cycle timers of this solver were removed with the round-2 solver; the macros stay as no-ops)
 #define DBG_T(i) do { (void)dbg_t0; } while (0)
 #define DBG_TB(i) do { (void)dbg_t0b; } while (0)
 #define DBG_CLOCK() 0ll
-#endif
 
 struct Parts {
   int P, base, rem;

@@ -37,6 +37,23 @@ namespace csdo {
 constexpr double kRhoMin = 1e-6, kRhoMax = 1e6, kRhoEqOverIneq = 1e3, kRhoTol = 1e-4;
 constexpr double kMinScaling = 1e-4, kMaxScaling = 1e4, kOsqpInfty = 1e30;
 constexpr int kBand = 6;        // half bandwidth of the reduced KKT in time-major order
+constexpr int kLw = kBand + 1;  // one-warp solver: stored entries per row (1/d_i and 6 sub-diagonals)
+
+// geometry of the one-warp solver used for horizons <= 96 steps (band_solver.cuh)
+constexpr int kMaxP = 16;                 // horizon partitions (lanes of the solver warp)
+constexpr int kMaxNs = 6 * (kMaxP - 1);   // separator unknowns
+constexpr int kL2Tinv = 4 * 18 * 18, kL2R = 18 * 18, kL2B = 6 * 36;  // level-2 inverses and couplings
+constexpr int kL2Doubles = kL2Tinv + kL2R + kL2B;
+constexpr int kSkewPad = 256;  // extra doubles at the end of the L6 area (<= 16 partitions x 14 doubles)
+constexpr int kOneWarpMaxNT = 128;        // block sizes up to this use the one-warp solver
+
+struct BandMem {
+  double *L6, *dinv;  // [(6t+k)*6 + d-1], [6t+k]; generic pointers (shared or global)
+  double *Sinv;       // level-2 inverses of the separator system, kL2Doubles (shared)
+  double *sv;         // 3 * kMaxNs scratch: g, x_sep, z / pivot rows (shared)
+  double *G;          // factor-time scratch: per partition GCC[21] GBB[21] GBC[36] = 78 * kMaxP doubles (shared)
+  const int *tab;     // bank-skew table of the partitions (shared context)
+};
 
 // read-only per-step planes (stride NT)
 enum Ro : int {
@@ -61,7 +78,11 @@ struct CtxShared {
   double *cfgs;  // 6 start/goal pins
   double *Es;    // Ruiz row scaling of the fixed rows, 16 planes (read-only during the ADMM loop)
   double *ws;    // ADMM row state w = z_hat + y/rho of the fixed rows, 16 planes
-  PbcrMem pm;    // reduced-KKT factor storage (pbcr_solver.cuh)
+  PbcrMem pm;    // reduced-KKT factor storage (pbcr_solver.cuh), horizons > 96
+  BandMem bm;    // ... of the one-warp solver (band_solver.cuh), horizons <= 96
+  int skew_tab[kMaxP];
+  int solver_warp;
+  void *fn_factor; // one-warp factorization entry point
   csdo_params P; // copy of the parameters for the out-of-line (cold) phases
   void *fn_solve; // band solve entry point (indirect call, see dsqp_kernel.cu)
   void *fn_sweep; // the sweeps alone (developer variants)
@@ -100,6 +121,7 @@ struct Ctx {
   CSDO_GET(const double *, obs) CSDO_GET(double *, corr) CSDO_GET(double, dimx) CSDO_GET(double, dimy)
 #undef CSDO_GET
   __device__ __forceinline__ const PbcrMem &pm() const { return s->pm; }
+  __device__ __forceinline__ const BandMem &bm() const { return s->bm; }
   // one thread per time step
   __device__ __forceinline__ int tid() const { return threadIdx.x; }
   __device__ __forceinline__ int nthr() const { return blockDim.x; }

@@ -8,6 +8,7 @@
 //   isFeasible / updateCorridor     sqp/dsqp_solver.cc:292-420, 818-872
 //   generateBox & co                sqp/corridor.cc:25-324
 #include "dsqp_device.cuh"
+#include "band_solver.cuh"
 #include "dsqp_launch.h"
 #include <cstdlib>
 
@@ -567,6 +568,36 @@ __device__ __forceinline__ void ruiz_scale(Ctx &c, const csdo_params &P) {
 
 // reduced KKT  H = c D P D + sigma I + D A_raw' diag(rho E^2) A_raw D  into the
 // band storage, then LDL'.
+// block t's row k of the band storage: rec[d], d = 1..6, is H_{i,i-d} (i = 6t + k), diag its H_ii slot.
+// OW: the one-warp solver's row storage (band_solver.cuh), else the block records of pbcr_solver.cuh.
+using OwSolveFn = void (*)(const BandMem, double *, double *, int, int);
+using OwFactorFn = void (*)(const BandMem, int);
+// register class RC of a kernel variant: 0 = 255 registers, 1 = 168, 2 = 128 with the CTA-wide solver
+// (pbcr_solver.cuh); 3 = 255, 4 = 168 with the one-warp solver (band_solver.cuh, block sizes <= 96)
+__host__ __device__ constexpr bool one_warp(int RC) { return RC >= 3; }
+#ifdef CSDO_OW_ROWS_COLD
+constexpr bool kOwRowsInline = false;
+#else
+constexpr bool kOwRowsInline = true;
+#endif
+
+template <bool OW>
+struct BandRow {
+  double *rec, *diag;
+  __device__ __forceinline__ BandRow(const Ctx &c, int t, int k) {
+    if (OW) {
+      const int sk = make_parts(c.Nt(), c.s->skew_tab).skew_of_block(t);
+      rec = c.bm().L6 + sk + (size_t)(6 * t + k) * 6 - 1;
+      diag = c.bm().dinv + 6 * t + k;
+    } else {
+      double *B = pbcr_blk(c.pm().L, t);
+      rec = B + 6 * k - 1;
+      diag = B + 36 + k;
+    }
+  }
+};
+
+template <bool OW>
 __device__ __forceinline__ void form_and_factor(Ctx &c, const csdo_params &P) {
   const int NT = c.NT(), t = c.t(), Nt = c.Nt();
   HasmF hf;
@@ -589,11 +620,13 @@ __device__ __forceinline__ void form_and_factor(Ctx &c, const csdo_params &P) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) c.carry()[k * NT + t] = hf.nd[k];
     // clear this step's block record; the last step's missing v, w are dummy unknowns (H_ii = 1)
-    double *B = pbcr_blk(c.pm().L, t);
 #pragma unroll
-    for (int i = 0; i < 36; ++i) B[i] = 0.0;
+    for (int k = 0; k < 6; ++k) {
+      const BandRow<OW> r(c, t, k);
 #pragma unroll
-    for (int k = 0; k < 6; ++k) B[36 + k] = 1.0;
+      for (int d = 1; d <= 6; ++d) r.rec[d] = 0.0;
+      *r.diag = 1.0;
+    }
   }
   __syncthreads();
   if (c.active()) {
@@ -605,28 +638,33 @@ __device__ __forceinline__ void form_and_factor(Ctx &c, const csdo_params &P) {
       hf.q[VV][VV] += c.c * ((t != 0 && t != Nt - 2) ? 2.0 : 1.0);
       hf.q[VW][VW] += c.c * 1.0;
     }
-    double *B = pbcr_blk(c.pm().L, t);
     for (int k = 0; k < nv; ++k) {
-      double *Lr = B + 6 * k - 1;  // Lr[d] = H_{i,i-d}
+      const BandRow<OW> r(c, t, k);  // r.rec[d] = H_{i,i-d}
       double diag = hf.q[k][k];
       if (k < 4 && t > 0) diag += c.carry()[k * NT + t - 1];
-      B[36 + k] = dk[k] * dk[k] * diag + P.sigma;
-      for (int j = 0; j < k; ++j) Lr[k - j] = dk[k] * dk[j] * hf.q[k][j];
+      *r.diag = dk[k] * dk[k] * diag + P.sigma;
+      for (int j = 0; j < k; ++j) r.rec[k - j] = dk[k] * dk[j] * hf.q[k][j];
     }
     if (c.has_next()) {
       const int nvn = (t + 1 < Nt - 1) ? 6 : 4;
-      double *Bn = pbcr_blk(c.pm().L, t + 1);
       for (int k = 0; k < 4; ++k) {  // rows x,y,yaw,steer of step t+1
-        double *Lr = Bn + 6 * k - 1;
-        for (int j = k; j < 6; ++j) Lr[6 + k - j] = dk[6 + k] * dk[j] * hf.cr[k][j];
+        const BandRow<OW> r(c, t + 1, k);
+        for (int j = k; j < 6; ++j) r.rec[6 + k - j] = dk[6 + k] * dk[j] * hf.cr[k][j];
       }
       if (nvn == 6)  // v_{t+1} - v_t coupling of the objective
-        (Bn + 6 * VV - 1)[6] = c.D()[VV * NT + t + 1] * dk[VV] * (-c.c);
+        BandRow<OW>(c, t + 1, VV).rec[6] = c.D()[VV * NT + t + 1] * dk[VV] * (-c.c);
     }
   }
   __syncthreads();
-  if (c.l_shared()) pbcr_factor_cta<true>(c.pm(), Nt);
-  else pbcr_factor_cta<false>(c.pm(), Nt);
+  if (OW) {
+    // one warp factors (the others wait): entered through a pointer so that it gets its own register budget
+    __syncwarp();
+    if ((c.tid() >> 5) == c.s->solver_warp) reinterpret_cast<OwFactorFn>(c.s->fn_factor)(c.bm(), Nt);
+    __syncthreads();
+  } else {
+    if (c.l_shared()) pbcr_factor_cta<true>(c.pm(), Nt);
+    else pbcr_factor_cta<false>(c.pm(), Nt);
+  }
 }
 
 // optional phase timing (thread 0's clock), accumulated per CTA and added to queue[2..] at exit
@@ -824,7 +862,7 @@ __device__ __noinline__ double ruiz_scale_cold(CtxShared *s) {
 template <int RC>
 __device__ __noinline__ void form_and_factor_cold(CtxShared *s, double rho, double cc) {
   Ctx c = make_ctx(s, rho, cc);
-  form_and_factor(c, s->P);
+  form_and_factor<one_warp(RC)>(c, s->P);
 }
 template <int RC>
 __device__ __noinline__ void assemble_rows_cold(CtxShared *s) {
@@ -873,6 +911,8 @@ __device__ __noinline__ void band_solve_call(CtxShared *s) {
 using BandSolveFn = void (*)(CtxShared *);
 __device__ BandSolveFn g_band_solve[3] = {band_solve_call<0>, band_solve_call<1>, band_solve_call<2>};
 __device__ PbcrSweepFn g_pbcr_sweep[2] = {pbcr_sweep_entry<false>, pbcr_sweep_entry<true>};
+__device__ OwSolveFn g_ow_solve[2] = {band_solve_warp<false>, band_solve_warp<true>};
+__device__ OwFactorFn g_ow_factor[2] = {band_factor_warp<false>, band_factor_warp<true>};
 
 // solveOSQP (dsqp_solver.cc:423-555): setup + warm start + ADMM; solution in c.sol()
 
@@ -914,8 +954,16 @@ __device__ __forceinline__ QpOut solve_qp(Ctx &c, const csdo_params &P, const La
       else pbcr_solve_cta<false, true>(pm, c.rhs(), c.xt(), Nt, NT, c.s->fn_solve);
     }
 #else
-    if (RC == 0) band_solve_call<RC>(c.s);
-    else reinterpret_cast<BandSolveFn>(c.s->fn_solve)(c.s);
+    if (one_warp(RC)) {
+      __syncwarp();  // the solver warp must enter the solve converged (threads leave barriers individually)
+      if ((c.tid() >> 5) == c.s->solver_warp)
+        reinterpret_cast<OwSolveFn>(c.s->fn_solve)(c.s->bm, c.rhs(), c.xt(), Nt, NT);
+      __syncthreads();
+    } else if (RC == 0) {
+      band_solve_call<0>(c.s);
+    } else {
+      reinterpret_cast<BandSolveFn>(c.s->fn_solve)(c.s);
+    }
 #endif
     PH_ADD(4);
     const bool can_check = P.check_termination && (iter % P.check_termination == 0);
@@ -924,6 +972,7 @@ __device__ __forceinline__ QpOut solve_qp(Ctx &c, const csdo_params &P, const La
 #ifdef CSDO_ROWS_INLINE   // (developer switch: the hot row pass inline measured 2-3 % slower than out of line)
     else step_rows<2, true>(c, P, store_dy, 0.0);
 #else
+    else if (one_warp(RC) && kOwRowsInline) step_rows<2, true>(c, P, store_dy, 0.0);
     else step_rows_cold<RC, 2, true>(c.s, c.rho, c.c, store_dy, 0.0);
 #endif
     PH_ADD(5);
@@ -1080,7 +1129,12 @@ __device__ __forceinline__ void refine_body(const DevBatch &B, const DevOut &O, 
 #ifdef CSDO_SWEEP_ONLY_INDIRECT
     cs.fn_solve = reinterpret_cast<void *>(*(volatile PbcrSweepFn *)&g_pbcr_sweep[(LY.tier & 2) ? 0 : 1]);
 #else
-    cs.fn_solve = reinterpret_cast<void *>(*(volatile BandSolveFn *)&g_band_solve[RC]);
+    if (one_warp(RC)) {
+      cs.fn_solve = reinterpret_cast<void *>(*(volatile OwSolveFn *)&g_ow_solve[(LY.tier & 2) ? 0 : 1]);
+      cs.fn_factor = reinterpret_cast<void *>(*(volatile OwFactorFn *)&g_ow_factor[(LY.tier & 2) ? 0 : 1]);
+    } else {
+      cs.fn_solve = reinterpret_cast<void *>(*(volatile BandSolveFn *)&g_band_solve[RC % 3]);
+    }
 #endif
     cs.fn_sweep = reinterpret_cast<void *>(*(volatile PbcrSweepFn *)&g_pbcr_sweep[(LY.tier & 2) ? 0 : 1]);
     cs.x = smem + LY.o_x; cs.xt = smem + LY.o_xt; cs.rhs = smem + LY.o_rhs; cs.D = smem + LY.o_D;
@@ -1099,6 +1153,14 @@ __device__ __forceinline__ void refine_body(const DevBatch &B, const DevOut &O, 
     cs.pm.g = cs.carry;                    // carry, xt are free while a solve runs
     cs.pm.y = cs.xt;
     cs.pm.xs = cs.xt + 6 * (NT / kPM);
+    if (one_warp(RC)) {   // the same areas, laid out for the one-warp solver (make_layout sizes them)
+      cs.bm.L6 = cs.pm.L;
+      cs.bm.dinv = cs.bm.L6 + 36 * NT + kSkewPad;
+      cs.bm.Sinv = smem + LY.o_sinv;
+      cs.bm.sv = cs.bm.Sinv + kL2Doubles;
+      cs.bm.tab = cs.skew_tab;
+      cs.bm.G = cs.xt;  // xt, rhs and carry are contiguous (16 NT doubles) and free while a factorization runs
+    }
     cs.cur = slot + LY.g_cur; cs.sol = slot + LY.g_sol; cs.dy = slot + LY.g_dy;
     cs.pl_glob = slot + LY.g_pl; cs.pl_smem = smem + LY.o_pl; cs.KS = LY.KS;
     cs.pc_glob = slot + LY.g_pc; cs.pc_smem = smem + LY.o_pc; cs.pc_cap = LY.PC;
@@ -1148,6 +1210,10 @@ __device__ __forceinline__ void refine_body(const DevBatch &B, const DevOut &O, 
     const int64_t off = B.agent_off[a];
     if (threadIdx.x == 0) {
       cs.Nt = Nt;
+      if (one_warp(RC)) {
+        fill_skew_table(Nt, cs.skew_tab);
+        cs.solver_warp = a % ((blockDim.x + 31) >> 5);
+      }
       cs.K = B.plane_ptr[a + 1] - B.plane_ptr[a];
       if (cs.K > LY.KMAX) {  // the caller understated max_planes: stay inside the scratch slot and flag it (csdo_sync)
         atomicExch(queue + kQError, 2);
@@ -1286,9 +1352,12 @@ template <int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
 dsqp_refine_kernel(const DevBatch B, const DevOut O, const csdo_params P, const Layout LY, double *scratch,
                    int *queue, const QueueState ST) {
-  // register class: 0 = 255 registers, 1 = 168 (three warps per sub-partition), 2 = 128 (four)
+  // register class: 0 = 255 registers, 1 = 168 (three warps per sub-partition), 2 = 128 (four); +3 for the
+  // block sizes that use the one-warp solver
   constexpr int kWarps = MAXT / 32 * MINB;
-  refine_body<(kWarps > 12) ? 2 : ((kWarps > 8) ? 1 : 0)>(B, O, P, LY, scratch, queue, ST);
+  constexpr int kRegs = (kWarps > 12) ? 2 : ((kWarps > 8) ? 1 : 0);
+  static_assert(MAXT > kOneWarpMaxNT || kRegs < 2, "no 128-register variant of the one-warp solver");
+  refine_body<(MAXT <= kOneWarpMaxNT) ? 3 + kRegs : kRegs>(B, O, P, LY, scratch, queue, ST);
 }
 
 using RefineKernel = void (*)(const DevBatch, const DevOut, const csdo_params, const Layout, double *, int *,
@@ -1381,8 +1450,10 @@ Layout make_layout(int NT, int KMAX, int tier, int KS, int PC, bool w_smem) {
   }
   l.o_red = take((((NT < 64 ? 64 : NT) + 31) / 32 + 1) * N_COUNT);  // one row per warp + the result row
   l.o_pstart = take((NT + 2 + 1) / 2);
-  l.o_sinv = take(pbcr_S_doubles(NT));
-  l.o_L = band_glob ? 0 : take(pbcr_L_doubles(NT));
+  const bool ow = NT <= kOneWarpMaxNT;   // the kernels with block size <= 96 use the one-warp solver's storage
+  const int L_doubles = ow ? kLw * 6 * NT + kSkewPad : pbcr_L_doubles(NT);
+  l.o_sinv = take(ow ? kL2Doubles + 3 * kMaxNs : pbcr_S_doubles(NT));
+  l.o_L = band_glob ? 0 : take(L_doubles);
   l.o_pl = take(PL_COUNT * 4 * KS);
   l.o_pc = take(PC);
   if (l.w_smem) l.o_w = take(16 * NT);  // tier 1 with room left: the rows' ADMM state w back on chip (read + written every pass)
@@ -1392,7 +1463,7 @@ Layout make_layout(int NT, int KMAX, int tier, int KS, int PC, bool w_smem) {
   l.g_cur = gtake(6 * (size_t)NT); l.g_sol = gtake(6 * (size_t)NT); l.g_dy = gtake(16 * (size_t)NT);
   l.g_pl = gtake((size_t)PL_COUNT * 4 * KMAX);
   l.g_pc = gtake((size_t)6 * KMAX);
-  l.g_L = gtake((size_t)pbcr_L_doubles(NT));
+  l.g_L = gtake((size_t)L_doubles);
   l.g_ro = gtake((size_t)RO_COUNT * NT + 8); l.g_E = gtake(16 * (size_t)NT); l.g_w = gtake(16 * (size_t)NT);
   l.slot_doubles = g;
   return l;
