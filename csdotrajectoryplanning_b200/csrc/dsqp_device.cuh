@@ -45,7 +45,7 @@ constexpr int kMaxNs = 6 * (kMaxP - 1);   // separator unknowns
 constexpr int kL2Tinv = 4 * 18 * 18, kL2R = 18 * 18, kL2B = 6 * 36;  // level-2 inverses and couplings
 constexpr int kL2Doubles = kL2Tinv + kL2R + kL2B;
 constexpr int kSkewPad = 256;  // extra doubles at the end of the L6 area (<= 16 partitions x 14 doubles)
-constexpr int kOneWarpMaxNT = 128;        // block sizes up to this use the one-warp solver
+constexpr int kOneWarpMaxNT = 96;         // block sizes up to this use the one-warp solver
 
 struct BandMem {
   double *L6, *dinv;  // [(6t+k)*6 + d-1], [6t+k]; generic pointers (shared or global)
