@@ -958,6 +958,10 @@ __device__ __forceinline__ QpOut solve_qp(Ctx &c, const csdo_params &P, const La
       __syncwarp();  // the solver warp must enter the solve converged (threads leave barriers individually)
       if ((c.tid() >> 5) == c.s->solver_warp)
         reinterpret_cast<OwSolveFn>(c.s->fn_solve)(c.s->bm, c.rhs(), c.xt(), Nt, NT);
+#ifdef CSDO_DOUBLE_SOLVE  // timing experiment: a second, discarded solve (its cost is the solve's share of the step)
+      if ((c.tid() >> 5) == c.s->solver_warp)
+        reinterpret_cast<OwSolveFn>(c.s->fn_solve)(c.s->bm, c.xt(), c.xt(), Nt, NT);
+#endif
       __syncthreads();
     } else if (RC == 0) {
       band_solve_call<0>(c.s);
@@ -1376,8 +1380,9 @@ static RefineKernel pick_kernel(int block, bool lean) {
   if (block <= 96) return lean ? dsqp_refine_kernel<96, 3> : dsqp_refine_kernel<96, 2>;
   if (block <= 128) return dsqp_refine_kernel<128, 2>;
   if (block <= 160 && lean) return dsqp_refine_kernel<160, 2>;
-  if (block <= 192 && lean) return dsqp_refine_kernel<192, 2>;
-  if (block <= 256 && lean) return dsqp_refine_kernel<256, 2>;
+  // (tried: <192,2> at 168 registers and <256,2> at 128 with the band factor in global scratch, i.e. two CTAs
+  // per SM for long horizons -- 53.8 k vs 55.3 k QP/s at Nt = 190 and 37.5 k vs 48.3 k at Nt = 256: the factor
+  // read from L2 inside the sweeps costs more than the second CTA brings)
   if (block <= 256) return dsqp_refine_kernel<256, 1>;
   return dsqp_refine_kernel<512, 1>;
 #endif
