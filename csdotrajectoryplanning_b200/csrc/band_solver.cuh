@@ -206,7 +206,7 @@ __device__ __forceinline__ double coupling(const double *L6, int tr, int kr, int
 }
 
 // ---- F2: Schur complement contributions of partition p, streamed ----
-__device__ void schur_partition(const BandMem &bm, const Parts &pt, int p) {
+static __device__ void schur_partition(const BandMem &bm, const Parts &pt, int p) {
   const double *L6 = bm.L6 + pt.skew(p), *dinv = bm.dinv;  // own rows and the next separator (same skew)
   const int t0 = pt.start(p), t1 = t0 + pt.len(p);
   double *GCC = bm.G + p * 78, *GBB = GCC + 21, *GBC = GBB + 21;

@@ -20,7 +20,7 @@
 namespace csdo {
 // developer counters: cycle timers, compiled in with -DCSDO_DEV_TIMERS (make DEV=-DCSDO_DEV_TIMERS) and
 // printed by csdo_refine when CSDO_PROFILE is set.  Thread 0 of every CTA accumulates clock64 deltas.
-__device__ unsigned long long g_dbg[32];
+static __device__ unsigned long long g_dbg[32];   // (one copy per translation unit)
 }
 #ifdef CSDO_DEV_TIMERS
 #define DBG_INIT() long long dbg_t_ = clock64()
@@ -79,10 +79,6 @@ struct CtxShared {
   double *Es;    // Ruiz row scaling of the fixed rows, 16 planes (read-only during the ADMM loop)
   double *ws;    // ADMM row state w = z_hat + y/rho of the fixed rows, 16 planes
   PbcrMem pm;    // reduced-KKT factor storage (pbcr_solver.cuh), horizons > 96
-  BandMem bm;    // ... of the one-warp solver (band_solver.cuh), horizons <= 96
-  int skew_tab[kMaxP];
-  int solver_warp;
-  void *fn_factor; // one-warp factorization entry point
   csdo_params P; // copy of the parameters for the out-of-line (cold) phases
   void *fn_solve; // band solve entry point (indirect call, see dsqp_kernel.cu)
   void *fn_sweep; // the sweeps alone (developer variants)
@@ -99,6 +95,12 @@ struct CtxShared {
   const double *obs;        // [No][3]
   double *corr;             // 8 planes, stride Nt (output array doubles as the live corridor)
   double dimx, dimy;
+  // one-warp solver (band_solver.cuh), horizons <= 96 (kept at the end: the offsets above are what the
+  // register allocation of the row passes was tuned with)
+  BandMem bm;
+  int skew_tab[kMaxP];
+  int solver_warp;
+  void *fn_factor; // one-warp factorization entry point
 };
 
 // Per-thread handle: the shared context plus the few values that change inside a QP.

@@ -7,6 +7,15 @@
 //                                   function-by-function correspondence)
 //   isFeasible / updateCorridor     sqp/dsqp_solver.cc:292-420, 818-872
 //   generateBox & co                sqp/corridor.cc:25-324
+//
+// This file is compiled TWICE (see the Makefile): -DCSDO_TU=1 holds the kernel variants for block sizes <= 96
+// (one-warp band solver, band_solver.cuh), -DCSDO_TU=2 the variants above (CTA-wide solver, pbcr_solver.cuh)
+// plus the small kernels and the host-side launchers.  Two modules because ptxas settles the calling
+// convention of the out-of-line phases per module: with both solvers' entry points address-taken in one
+// module, the 255-register kernels' hot row pass went from 64 to 184 B of register saves (-4 % at Nt = 256).
+#if !defined(CSDO_TU) || CSDO_TU < 1 || CSDO_TU > 2
+#error "compile with -DCSDO_TU=1 and -DCSDO_TU=2 (see the Makefile)"
+#endif
 #include "dsqp_device.cuh"
 #include "band_solver.cuh"
 #include "dsqp_launch.h"
@@ -46,7 +55,7 @@ constexpr int kMaxCand = 40;
 // generateLocalBox :278-324.  Only obstacles that can ever touch a box grown
 // from (xc,yc) are kept as candidates (a conservative superset, so the
 // sequence of accepted expansions is unchanged).
-__device__ bool local_box(double xc, double yc, const ObsView &ov, double dimx, double dimy,
+static __device__ bool local_box(double xc, double yc, const ObsView &ov, double dimx, double dimy,
                           const csdo_params &P, Box &res) {
   short *cand = ov.cand;  // per-thread slice (shared memory inside the refine kernel)
   int ncand = 0;
@@ -128,7 +137,7 @@ __device__ bool local_box(double xc, double yc, const ObsView &ov, double dimx, 
 
 // generateBox :124-159 (+ isPointOutOfMap :25-30, projectNearBorder :54-81,
 // isPointCollision :32-52, generateLegalPoint :84-122)
-__device__ void generate_box(double x, double y, const ObsView &ov, double dimx, double dimy,
+static __device__ void generate_box(double x, double y, const ObsView &ov, double dimx, double dimy,
                              const csdo_params &P, Box &box, int &success, int &initial) {
   const double rv = ov.rv;
   initial = 0;
@@ -173,7 +182,7 @@ __device__ void generate_box(double x, double y, const ObsView &ov, double dimx,
 
 // calcCorridors (float centres) / updateCorridor (double centres) for the
 // agent of this CTA: 2 boxes per step, strided over the CTA's threads.
-__device__ int agent_corridors(const Ctx &c, const csdo_params &P, const double *xs, const double *ys,
+static __device__ int agent_corridors(const Ctx &c, const csdo_params &P, const double *xs, const double *ys,
                                const double *yaws, double *stage, int stage_doubles, bool double_centres,
                                int *box_status) {
   // Stage the instance's obstacles and the per-thread candidate lists in shared memory that is idle
@@ -659,7 +668,14 @@ __device__ __forceinline__ void form_and_factor(Ctx &c, const csdo_params &P) {
   if (OW) {
     // one warp factors (the others wait): entered through a pointer so that it gets its own register budget
     __syncwarp();
+#ifdef CSDO_OW_DIRECT
+    if ((c.tid() >> 5) == c.s->solver_warp) {
+      if (c.l_shared()) band_factor_warp<true>(c.bm(), Nt);
+      else band_factor_warp<false>(c.bm(), Nt);
+    }
+#else
     if ((c.tid() >> 5) == c.s->solver_warp) reinterpret_cast<OwFactorFn>(c.s->fn_factor)(c.bm(), Nt);
+#endif
     __syncthreads();
   } else {
     if (c.l_shared()) pbcr_factor_cta<true>(c.pm(), Nt);
@@ -815,7 +831,7 @@ __device__ __forceinline__ void check_rows(Ctx &c, const csdo_params &P, bool wi
 }
 
 // check_termination (OSQP auxil.c); returns status or 0 when not terminated
-__device__ int termination_status(const Ctx &c, const csdo_params &P, const CheckOut &co, bool approximate) {
+static __device__ int termination_status(const Ctx &c, const csdo_params &P, const CheckOut &co, bool approximate) {
   const double cinv = 1.0 / c.c;
   double eps_abs = P.eps_abs, eps_rel = P.eps_rel, eps_pinf = P.eps_prim_inf;
   const double pri_res = co.nrm[N_PRI_U], dua_res = cinv * co.nrm[N_DUA_U];
@@ -888,9 +904,8 @@ __device__ __noinline__ int termination_status_cold(CtxShared *s, double cc, con
 // The band solve as its own function.  Its sweeps want ~200 registers; a noinline function called directly is
 // capped by what is live in its caller (1.1 KB of spills inside the sweeps), while a call through a function
 // pointer read from device memory follows the full ABI and gives the callee the whole register file.  Which
-// part goes behind the pointer depends on the register class, see the body.  Tried as well
-// (-DCSDO_SWEEP_ONLY_INDIRECT): the sweeps behind the pointer and the rest of the solve inline in the ADMM
-// loop -- 2-4 % slower on every workload.
+// part goes behind the pointer depends on the register class, see the body.  Tried as well: the sweeps behind
+// the pointer and the rest of the solve inline in the ADMM loop -- 2-4 % slower on every workload.
 template <int RC>
 __device__ __noinline__ void band_solve_call(CtxShared *s) {
   __builtin_assume(__isShared(s));
@@ -909,10 +924,20 @@ __device__ __noinline__ void band_solve_call(CtxShared *s) {
   }
 }
 using BandSolveFn = void (*)(CtxShared *);
+// The function-pointer tables are per translation unit ON PURPOSE (see the note at the top of this file): with
+// the one-warp solver's entry points address-taken in the same module, ptxas gave every out-of-line phase of
+// the 255-register kernels a larger save area (step_rows_cold: 64 -> 184 B of spills) and Nt = 256 lost 4 %.
+#if CSDO_TU == 2
+// (band_solve_call<0> is called directly but stays in the table: with its address not taken -- a third module
+// for the 168- / 128-register variants was tried -- it needs no register saves itself and its callers save
+// more instead, 1.5-2.7 % slower at Nt = 128..256)
 __device__ BandSolveFn g_band_solve[3] = {band_solve_call<0>, band_solve_call<1>, band_solve_call<2>};
 __device__ PbcrSweepFn g_pbcr_sweep[2] = {pbcr_sweep_entry<false>, pbcr_sweep_entry<true>};
+#endif
+#if CSDO_TU == 1 && !defined(CSDO_OW_DIRECT)
 __device__ OwSolveFn g_ow_solve[2] = {band_solve_warp<false>, band_solve_warp<true>};
 __device__ OwFactorFn g_ow_factor[2] = {band_factor_warp<false>, band_factor_warp<true>};
+#endif
 
 // solveOSQP (dsqp_solver.cc:423-555): setup + warm start + ADMM; solution in c.sol()
 
@@ -947,28 +972,27 @@ __device__ __forceinline__ QpOut solve_qp(Ctx &c, const csdo_params &P, const La
   int iter = 0;
   PH_ADD(5);
   for (iter = 1; iter <= P.osqp_max_iter; ++iter) {
-#ifdef CSDO_SWEEP_ONLY_INDIRECT
-    {
-      const PbcrMem pm = c.s->pm;
-      if (c.l_shared()) pbcr_solve_cta<true, true>(pm, c.rhs(), c.xt(), Nt, NT, c.s->fn_solve);
-      else pbcr_solve_cta<false, true>(pm, c.rhs(), c.xt(), Nt, NT, c.s->fn_solve);
-    }
-#else
-    if (one_warp(RC)) {
+    if constexpr (one_warp(RC)) {
       __syncwarp();  // the solver warp must enter the solve converged (threads leave barriers individually)
+#ifdef CSDO_OW_DIRECT   // (developer switch: direct calls instead of the function pointers)
+      if ((c.tid() >> 5) == c.s->solver_warp) {
+        if (c.l_shared()) band_solve_warp<true>(c.s->bm, c.rhs(), c.xt(), Nt, NT);
+        else band_solve_warp<false>(c.s->bm, c.rhs(), c.xt(), Nt, NT);
+      }
+#else
       if ((c.tid() >> 5) == c.s->solver_warp)
         reinterpret_cast<OwSolveFn>(c.s->fn_solve)(c.s->bm, c.rhs(), c.xt(), Nt, NT);
+#endif
 #ifdef CSDO_DOUBLE_SOLVE  // timing experiment: a second, discarded solve (its cost is the solve's share of the step)
       if ((c.tid() >> 5) == c.s->solver_warp)
         reinterpret_cast<OwSolveFn>(c.s->fn_solve)(c.s->bm, c.xt(), c.xt(), Nt, NT);
 #endif
       __syncthreads();
-    } else if (RC == 0) {
+    } else if constexpr (RC == 0) {
       band_solve_call<0>(c.s);
     } else {
       reinterpret_cast<BandSolveFn>(c.s->fn_solve)(c.s);
     }
-#endif
     PH_ADD(4);
     const bool can_check = P.check_termination && (iter % P.check_termination == 0);
     const bool store_dy = keep_dy && (can_check || iter == P.osqp_max_iter);
@@ -1130,17 +1154,18 @@ __device__ __forceinline__ void refine_body(const DevBatch &B, const DevOut &O, 
   if (threadIdx.x == 0) {
     cs.NT = LY.NT; cs.KP = 4 * LY.KMAX;
     cs.P = P;
-#ifdef CSDO_SWEEP_ONLY_INDIRECT
-    cs.fn_solve = reinterpret_cast<void *>(*(volatile PbcrSweepFn *)&g_pbcr_sweep[(LY.tier & 2) ? 0 : 1]);
-#else
-    if (one_warp(RC)) {
-      cs.fn_solve = reinterpret_cast<void *>(*(volatile OwSolveFn *)&g_ow_solve[(LY.tier & 2) ? 0 : 1]);
-      cs.fn_factor = reinterpret_cast<void *>(*(volatile OwFactorFn *)&g_ow_factor[(LY.tier & 2) ? 0 : 1]);
-    } else {
-      cs.fn_solve = reinterpret_cast<void *>(*(volatile BandSolveFn *)&g_band_solve[RC % 3]);
-    }
+#if CSDO_TU == 1
+    static_assert(one_warp(RC), "translation unit 1 holds the one-warp variants only");
+#ifndef CSDO_OW_DIRECT
+    cs.fn_solve = reinterpret_cast<void *>(*(volatile OwSolveFn *)&g_ow_solve[(LY.tier & 2) ? 0 : 1]);
+    cs.fn_factor = reinterpret_cast<void *>(*(volatile OwFactorFn *)&g_ow_factor[(LY.tier & 2) ? 0 : 1]);
 #endif
+    cs.fn_sweep = nullptr;
+#else
+    static_assert(!one_warp(RC), "translation unit 2 holds the CTA-wide variants only");
+    cs.fn_solve = reinterpret_cast<void *>(*(volatile BandSolveFn *)&g_band_solve[RC]);
     cs.fn_sweep = reinterpret_cast<void *>(*(volatile PbcrSweepFn *)&g_pbcr_sweep[(LY.tier & 2) ? 0 : 1]);
+#endif
     cs.x = smem + LY.o_x; cs.xt = smem + LY.o_xt; cs.rhs = smem + LY.o_rhs; cs.D = smem + LY.o_D;
     cs.carry = smem + LY.o_carry; cs.red = smem + LY.o_red;
     const bool rows_glob = LY.tier & 1;
@@ -1368,16 +1393,21 @@ using RefineKernel = void (*)(const DevBatch, const DevOut, const csdo_params, c
                               const QueueState);
 // lean: the variant compiled for one more resident CTA per SM.  Registers are allocated per SM
 // sub-partition (16384 each): 9 or 10 resident warps put 3 on one sub-partition, i.e. <= 168 per thread.
-static RefineKernel pick_kernel(int block, bool lean) {
-#ifdef CSDO_DEV_FAST  // developer builds: only the two 96-thread variants (short compile)
-#ifdef CSDO_DEV_ONE
-  return dsqp_refine_kernel<96, 2>;
-#else
-  return lean ? dsqp_refine_kernel<96, 3> : dsqp_refine_kernel<96, 2>;
-#endif
-#else
+#if CSDO_TU == 1
+RefineKernel pick_kernel_short(int block, bool lean) {   // block sizes <= 96
   if (block <= 64) return dsqp_refine_kernel<64, 4>;
-  if (block <= 96) return lean ? dsqp_refine_kernel<96, 3> : dsqp_refine_kernel<96, 2>;
+  return lean ? dsqp_refine_kernel<96, 3> : dsqp_refine_kernel<96, 2>;
+}
+void read_debug_counters_short(unsigned long long *out32) {
+  cudaMemcpyFromSymbol(out32, g_dbg, 32 * sizeof(unsigned long long));
+  unsigned long long z[32] = {0};
+  cudaMemcpyToSymbol(g_dbg, z, sizeof(z));
+}
+#else
+RefineKernel pick_kernel_short(int block, bool lean);       // translation unit 1
+void read_debug_counters_short(unsigned long long *out32);
+static RefineKernel pick_kernel(int block, bool lean) {
+  if (block <= kOneWarpMaxNT) return pick_kernel_short(block, lean);
   if (block <= 128) return dsqp_refine_kernel<128, 2>;
   if (block <= 160 && lean) return dsqp_refine_kernel<160, 2>;
   // (tried: <192,2> at 168 registers and <256,2> at 128 with the band factor in global scratch, i.e. two CTAs
@@ -1385,7 +1415,6 @@ static RefineKernel pick_kernel(int block, bool lean) {
   // read from L2 inside the sweeps costs more than the second CTA brings)
   if (block <= 256) return dsqp_refine_kernel<256, 1>;
   return dsqp_refine_kernel<512, 1>;
-#endif
 }
 
 // status aggregation of SolverDSQP (dsqp_solver.cc:1224-1243), one thread per instance
@@ -1533,10 +1562,12 @@ int refine_occupancy(int block, int smem_bytes, bool lean) {
   return n;
 }
 
-void read_debug_counters(unsigned long long *out16) {
-  cudaMemcpyFromSymbol(out16, g_dbg, 32 * sizeof(unsigned long long));
+void read_debug_counters(unsigned long long *out32) {   // both translation units' counters, summed
+  cudaMemcpyFromSymbol(out32, g_dbg, 32 * sizeof(unsigned long long));
   unsigned long long z[32] = {0};
   cudaMemcpyToSymbol(g_dbg, z, sizeof(z));
+  read_debug_counters_short(z);
+  for (int i = 0; i < 32; ++i) out32[i] += z[i];
 }
 
 int refine_kernel_regs(int block, bool lean) {
@@ -1544,5 +1575,7 @@ int refine_kernel_regs(int block, bool lean) {
   if (cudaFuncGetAttributes(&fa, pick_kernel(block, lean)) != cudaSuccess) return -1;
   return fa.numRegs;
 }
+
+#endif  // CSDO_TU == 2 (else branch of the pick_kernel block)
 
 }  // namespace csdo

@@ -5,7 +5,8 @@ name=$1; shift
 NVCC=/usr/local/cuda/bin/nvcc
 ARCH="-gencode arch=compute_100a,code=sm_100a"
 COMMON="$* -O3 -std=c++17 -lineinfo $ARCH -I../../include -I. -Xcompiler -fPIC -ccbin /usr/bin/g++"
-$NVCC $COMMON -c dsqp_kernel.cu -o _dev/_obj/dsqp_kernel.o &
+$NVCC $COMMON -DCSDO_TU=1 -c dsqp_kernel.cu -o _dev/_obj/dsqp_kernel_short.o &
+$NVCC $COMMON -DCSDO_TU=2 -c dsqp_kernel.cu -o _dev/_obj/dsqp_kernel_wide.o &
 $NVCC $COMMON -fmad=false -c planes_kernel.cu -o _dev/_obj/planes_kernel.o &
 $NVCC $COMMON -c csdo_api.cu -o _dev/_obj/csdo_api.o &
 $NVCC $COMMON -c measure_kernel.cu -o _dev/_obj/measure_kernel.o &
