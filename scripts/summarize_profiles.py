@@ -49,7 +49,15 @@ tj[f"dram_bytes_per_agent_step_{wl}"] = tr / steps
 tj["source"] = f"profiles/{tag}_refine_full_summary.txt (ncu --set full, one launch of a {wl} sub-batch, {steps} agent steps)"
 tj["git"] = git
 json.dump(tj, open("profiles/traffic.json", "w"), indent=1)
+st = {a[len("smsp__pcsamp_warps_issue_stalled_"):]: float(c.replace(",", "")) for a, b, c in zip(rr[0], rr[1], rr[2])
+      if a.startswith("smsp__pcsamp_warps_issue_stalled_") and "not_issued" not in a}
+stot = sum(st.values()) or 1.0
+stalls = "\n".join(f"warp_samples_{k} = {100 * v / stot:.1f} %" for k, v in sorted(st.items(), key=lambda kv: -kv[1])[:8])
+extra = ["lts__t_sectors_srcunit_tex_op_read.sum", "lts__t_sectors_srcunit_tex_op_write.sum",
+         "l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum",
+         "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum"]
+more = "\n".join(f"{a} = {c} {b}" for a, b, c in zip(rr[0], rr[1], rr[2]) if a in extra)
 open(f"profiles/{tag}_refine_full_summary.txt", "w").write(
     f"# ncu --set full --clock-control none -k regex:dsqp_refine -c 1 python bench.py --workload {wl} --steps 1 --no-cpu-baseline (git {git})\n"
-    + "\n".join(f"{k} = {summ[k][0]} {summ[k][1]}" for k in want if k in summ) + f"\ndram_bytes_per_launch = {tr:.0f}\nagent_steps_per_launch = {steps}\n")
+    + "\n".join(f"{k} = {summ[k][0]} {summ[k][1]}" for k in want if k in summ) + f"\ndram_bytes_per_launch = {tr:.0f}\nagent_steps_per_launch = {steps}\n" + more + "\n# warp state samples (pc sampling), share of all samples\n" + stalls + "\n")
 print(open(f"profiles/{tag}_refine_full_summary.txt").read())
