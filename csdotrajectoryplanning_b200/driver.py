@@ -19,7 +19,7 @@ import numpy as np
 
 from . import verdict as V
 from .batch import Instance, pack_instances
-from .output import SolutionStatistics, dump_solutions, load_solutions
+from .output import SolutionStatistics, dump_corridors, dump_solutions, load_solutions
 from .scenario import load_scenario_yaml
 
 
@@ -62,8 +62,9 @@ def collect_mapset(scenario_paths: Sequence[str], guess_dir: str) -> List[Instan
 
 
 def run_mapset(instances: Sequence[Instance], solver, out_dir: Optional[str] = None,
-               check_collisions: bool = True) -> MapsetReport:
-    """One batch through planes + refine; optional solution files (dumpSolutions format) and verdicts."""
+               check_collisions: bool = True, dump_corridor: bool = False) -> MapsetReport:
+    """One batch through planes + refine; optional solution files (dumpSolutions format) and verdicts.
+    dump_corridor: also write <name>_corridors.yaml like `./csdo --dump_corridor` (csdo.cc:163-165)."""
     batch = pack_instances(list(instances))
     batch, inter_legal = solver.planes(batch)
     t0 = time.perf_counter()
@@ -88,6 +89,12 @@ def run_mapset(instances: Sequence[Instance], solver, out_dir: Optional[str] = N
             path = os.path.join(out_dir, (instances[i].name or f"instance{i}") + ".yaml")
             dump_solutions(path, trajs, stat)
             rep.files.append(path)
+            if dump_corridor:
+                corr = np.stack([res.agent_corridor(batch, a) for a in range(a0, a1)])
+                nt = int(batch.inst_nt[i])
+                guess = np.stack([batch.guess[6 * batch.agent_off[a]:6 * batch.agent_off[a + 1]].reshape(6, nt)
+                                  for a in range(a0, a1)])
+                dump_corridors(path[:-5] + "_corridors.yaml", corr, guess, solver.params.f2x, solver.params.r2x)
     return rep
 
 

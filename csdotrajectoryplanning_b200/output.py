@@ -66,6 +66,34 @@ def format_solutions(trajs: np.ndarray, stat: SolutionStatistics) -> str:
     return "\n".join(out) + "\n"
 
 
+def format_corridors(corridors: np.ndarray, guess: np.ndarray, f2x: float, r2x: float) -> str:
+    """The file `./csdo --dump_corridor` writes (dumpCorridors, sqp/utils.cc:62-89).  corridors: (Na, 8, Nt)
+    planes xf_min, xf_max, yf_min, yf_max, xr_min, xr_max, yr_min, yr_max; guess: (Na, >=3, Nt) planes x, y, yaw of
+    x0_bar.  Per agent and step two rows "[disc centre x, y, x_min, x_max, y_min, y_max]" (front, rear) in the
+    stream's default format (6 significant digits); the centres pass through State's float members."""
+    corridors, guess = np.asarray(corridors, np.float64), np.asarray(guess, np.float64)
+    na, _, nt = corridors.shape
+    g = lambda v: f"{float(v):.6g}"
+    f2, r2 = np.float64(np.float32(f2x)), np.float64(np.float32(r2x))
+    out = []
+    for a in range(na):
+        out.append(f"agent{a}:")
+        x, y, yaw = guess[a][0], guess[a][1], guess[a][2]
+        c = corridors[a]
+        for t in range(nt):
+            cs, sn = np.cos(yaw[t]), np.sin(yaw[t])
+            xf, yf = np.float32(x[t] + f2 * cs), np.float32(y[t] + f2 * sn)
+            xr, yr = np.float32(x[t] + r2 * cs), np.float32(y[t] + r2 * sn)
+            out.append(f"  - [{g(xf)}, {g(yf)}, {g(c[0][t])}, {g(c[1][t])}, {g(c[2][t])}, {g(c[3][t])}]")
+            out.append(f"  - [{g(xr)}, {g(yr)}, {g(c[4][t])}, {g(c[5][t])}, {g(c[6][t])}, {g(c[7][t])}]")
+    return "\n".join(out) + "\n"
+
+
+def dump_corridors(path: str, corridors: np.ndarray, guess: np.ndarray, f2x: float, r2x: float) -> None:
+    with open(path, "w") as f:
+        f.write(format_corridors(corridors, guess, f2x, r2x))
+
+
 def dump_solutions(path: str, trajs: np.ndarray, stat: SolutionStatistics) -> None:
     with open(path, "w") as f:
         f.write(format_solutions(trajs, stat))

@@ -4,6 +4,7 @@
 // scripts/analysis_result.py and scripts/visualize.py read unchanged.
 #pragma once
 
+#include <cmath>
 #include <fstream>
 #include <iomanip>
 #include <string>
@@ -57,6 +58,28 @@ inline void dumpSolutions(const std::string &file_name, const std::vector<std::v
       if (t == Nt - 1) continue;
       out << "      v: " << s.v << "\n"
           << "      omega: " << s.d_steer * 180 / 3.14 << "\n";
+    }
+  }
+}
+
+// Corridor file of `./csdo --dump_corridor` (dumpCorridors, sqp/utils.cc:62-89): per agent and step two rows
+// "[disc centre x, y, x_min, x_max, y_min, y_max]" (front disc, rear disc) of the INITIAL GUESS x0_bar, in the
+// stream's default 6-significant-digit format; the centres go through State's float members
+// (common/motion_planning.h:115-118, 201-206).  f2x / r2x: the float Constants (csdo_params::f2x, r2x).
+inline void dumpCorridors(const std::string &file_name, const std::vector<std::vector<Corridor>> &corridors,
+                          const std::vector<std::vector<OptimizeResult>> &x0_bar, double f2x = 1.25, double r2x = -0.25) {
+  std::ofstream out(file_name);
+  const size_t Na = corridors.size();
+  const size_t Nt = Na ? corridors[0].size() : 0;
+  for (size_t a = 0; a < Na; ++a) {
+    out << "agent" << a << ":" << std::endl;
+    for (size_t t = 0; t < Nt; ++t) {
+      const OptimizeResult &s = x0_bar[a][t];
+      const Corridor &c = corridors[a][t];
+      const double xf = (float)(s.x + (float)f2x * std::cos(s.yaw)), yf = (float)(s.y + (float)f2x * std::sin(s.yaw));
+      const double xr = (float)(s.x + (float)r2x * std::cos(s.yaw)), yr = (float)(s.y + (float)r2x * std::sin(s.yaw));
+      out << "  - [" << xf << ", " << yf << ", " << c.xf_min << ", " << c.xf_max << ", " << c.yf_min << ", " << c.yf_max << "]\n";
+      out << "  - [" << xr << ", " << yr << ", " << c.xr_min << ", " << c.xr_max << ", " << c.yr_min << ", " << c.yr_max << "]\n";
     }
   }
 }

@@ -17,11 +17,12 @@ ap.add_argument("--scenarios", nargs="+", required=True)
 ap.add_argument("--guesses", required=True)
 ap.add_argument("--out", required=True)
 ap.add_argument("--device", type=int, default=0)
+ap.add_argument("--dump-corridor", action="store_true", help="also write <name>_corridors.yaml (csdo.cc:163-165)")
 a = ap.parse_args()
 inst = collect_mapset(a.scenarios, a.guesses)
 if not inst:
     sys.exit("no scenario with a matching guess file")
-rep = run_mapset(inst, DsqpSolver(default_params(), device=a.device), a.out)
+rep = run_mapset(inst, DsqpSolver(default_params(), device=a.device), a.out, dump_corridor=a.dump_corridor)
 s = rep.summary()
 json.dump({**s, "per_instance": [{"name": n, "solver_status": int(st), "search_status": int(ss), "collisions": int(c)}
                                  for n, st, ss, c in zip(rep.names, rep.solver_status, rep.search_status, rep.collisions)]},

@@ -18,6 +18,7 @@ class _OracleSolver:
 
     def __init__(self, oracle, params):
         self.o, self.p = oracle, params
+        self.params = params
 
     def planes(self, batch):
         inst = batch.unpack()
@@ -48,8 +49,13 @@ def test_mapset_driver_host_logic(tmp_path, oracle, params):
     inst = collect_mapset([str(sdir)], str(gdir))
     assert [i.name for i in inst] == ["map_50by50_obst6_agents3_ex0", "map_50by50_obst6_agents4_ex1"]
     assert inst[0].guess.shape[0] == 3 and inst[1].guess.shape[0] == 4 and inst[0].obstacles.shape == (6, 3)
-    rep = run_mapset(inst, _OracleSolver(oracle, params), str(odir))
+    rep = run_mapset(inst, _OracleSolver(oracle, params), str(odir), dump_corridor=True)
     assert len(rep.files) == 2 and all(os.path.exists(f) for f in rep.files)
+    # --dump_corridor files: "agent<a>:" + two rows per step, readable as YAML
+    cdoc = yaml.safe_load(open(rep.files[0][:-5] + "_corridors.yaml"))
+    assert sorted(cdoc) == ["agent0", "agent1", "agent2"] and len(cdoc["agent0"]) == 2 * inst[0].guess.shape[2]
+    row = cdoc["agent1"][0]
+    assert len(row) == 6 and row[2] <= row[0] <= row[3] and row[4] <= row[1] <= row[5]   # the disc centre is inside its box
     for i, f in enumerate(rep.files):
         st, ok = read_solution_status(f)
         assert st.solver_status == int(rep.solver_status[i]) and ok == bool(rep.success[i])

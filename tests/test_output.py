@@ -72,3 +72,33 @@ def test_cpp_dump_solutions_writes_the_same_file(tmp_path):
     subprocess.run([os.path.join(here, "cpp", "test_solution_io"), path], input="\n".join(lines) + "\n", text=True,
                    check=True)
     assert open(path).read() == format_solutions(tr, stat)
+
+
+def test_dump_corridors_cpp_and_python_agree(tmp_path):
+    """dumpCorridors (sqp/utils.cc:62-89; restated, the file itself needs Eigen/OSQP headers so it is not part of
+    oracle/_ref): C++ header and Python writer give the same text, with a hand-checked first row."""
+    import os, subprocess
+    from csdotrajectoryplanning_b200 import default_params
+    from csdotrajectoryplanning_b200.output import format_corridors
+    here = os.path.dirname(os.path.abspath(__file__))
+    subprocess.run(["make", "-C", os.path.join(here, "cpp"), "test_solution_io"], check=True, capture_output=True)
+    p = default_params()
+    rng = np.random.default_rng(5)
+    na, nt = 2, 5
+    guess = np.stack([rng.uniform(0, 100, (na, nt)), rng.uniform(0, 100, (na, nt)), rng.uniform(-3.2, 3.2, (na, nt))], axis=1)
+    guess[0, :, 0] = (10.0, 20.0, 0.0)                    # front disc at (11.25, 20), rear at (9.75, 20)
+    corr = guess[:, [0, 0, 1, 1, 0, 0, 1, 1], :] + rng.uniform(-10, 10, (na, 8, nt))
+    corr[0, :, 0] = (8.5, 14.0, 17.123456789, 23.0, 1e-7, 12.0, 17.0, 1234567.0)
+    lines = [f"{na} {nt} {p.f2x!r} {p.r2x!r}"]
+    for a in range(na):
+        for t in range(nt):
+            lines.append(" ".join(repr(float(v)) for v in list(guess[a, :, t]) + list(corr[a, :, t])))
+    path = str(tmp_path / "corridors.yaml")
+    subprocess.run([os.path.join(here, "cpp", "test_solution_io"), path, "corridors"], input="\n".join(lines) + "\n",
+                   text=True, check=True)
+    text = format_corridors(corr, guess, p.f2x, p.r2x)
+    assert open(path).read() == text
+    rows = text.split("\n")
+    assert rows[0] == "agent0:"
+    assert rows[1] == "  - [11.25, 20, 8.5, 14, 17.1235, 23]"
+    assert rows[2] == "  - [9.75, 20, 1e-07, 12, 17, 1.23457e+06]"
