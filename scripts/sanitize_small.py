@@ -10,6 +10,8 @@ p = default_params()
 which = sys.argv[1] if len(sys.argv) > 1 else "short"
 if which == "short":
     inst = [synthetic_instance(7, 50.0, 4, 10, (8, 12), p), synthetic_instance(8, 50.0, 3, 0, (27, 29), p)]
+elif which == "dense":   # a small map: many inter-vehicle planes per agent (plane-major passes)
+    inst = [synthetic_instance(11, 25.0, 6, 4, (9, 12), p)]
 elif which == "long":
     inst = [synthetic_instance(9, 60.0, 3, 6, (41, 42), p)]
 else:
