@@ -294,42 +294,6 @@ __device__ __forceinline__ void visit_rows(Ctx &c, const csdo_params &P, F &f) {
 // IN selects the per-step input: the current iterate D x (xt), D x~ right after a solve (D, rhs), D itself.
 enum PlaneIn : int { IN_NONE = 0, IN_XT, IN_DXT, IN_D };
 
-// The hot ADMM row pass asks for the record and the step index of the thread's FIRST plane ahead of time (L1
-// prefetches issued together with the fixed rows' loads), so that the plane pass does not start with an L2
-// round trip of its own: 10 % of all warp samples of the Nt = 256 kernel sat on the first use of plane_t.
-// (Holding the record in registers across the fixed rows instead spilled 0.8 KB per thread: -8 %.)
-__device__ __forceinline__ void planes_prefetch_first(const Ctx &c) {
-  if (c.tid() < c.K() && c.pl() != c.pl_smem()) {
-    const char *q = reinterpret_cast<const char *>(c.pl() + (size_t)PL_COUNT * 4 * c.tid());  // 192 B, 64-B aligned
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(q + 128));
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(c.plane_t() + c.tid()));
-  }
-}
-__device__ __forceinline__ void planes_load_record(const Ctx &c, int k, double (&v)[4][PL_COUNT]) {
-  const double2 *q2 = reinterpret_cast<const double2 *>(c.pl() + (size_t)PL_COUNT * 4 * k);
-  if (c.pl() == c.pl_smem()) {
-    __builtin_assume(__isShared(q2));
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int h = 0; h < PL_COUNT / 2; ++h) {
-        const double2 d2 = q2[r * (PL_COUNT / 2) + h];
-        v[r][2 * h] = d2.x;
-        v[r][2 * h + 1] = d2.y;
-      }
-  } else {
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int h = 0; h < PL_COUNT / 2; ++h) {
-        const double2 d2 = q2[r * (PL_COUNT / 2) + h];
-        v[r][2 * h] = d2.x;
-        v[r][2 * h + 1] = d2.y;
-      }
-  }
-}
-
 template <int IN, class F>
 __device__ __forceinline__ void visit_planes(Ctx &c, const csdo_params &P, F &f) {
   const int K = c.K();
@@ -339,10 +303,30 @@ __device__ __forceinline__ void visit_planes(Ctx &c, const csdo_params &P, F &f)
   // contribution buffer: the solve scratch xt (6 NT doubles, idle in every pass that does not read the iterate
   // from it), else the dedicated shared-memory buffer, else global scratch
   double *pc = (IN != IN_XT && NOUT * K <= 6 * NT) ? c.xt() : ((NOUT * K <= c.pc_cap()) ? c.pc_smem() : c.pc_glob());
+  const bool on_chip = c.pl() == c.pl_smem();
   for (int k = c.tid(); k < K; k += c.nthr()) {
     double2 *q2 = reinterpret_cast<double2 *>(c.pl() + (size_t)PL_COUNT * 4 * k);
     double v[4][PL_COUNT];
-    planes_load_record(c, k, v);
+    if (on_chip) {
+      __builtin_assume(__isShared(q2));
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int h = 0; h < PL_COUNT / 2; ++h) {
+          const double2 d2 = q2[r * (PL_COUNT / 2) + h];
+          v[r][2 * h] = d2.x;
+          v[r][2 * h + 1] = d2.y;
+        }
+    } else {
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int h = 0; h < PL_COUNT / 2; ++h) {
+          const double2 d2 = q2[r * (PL_COUNT / 2) + h];
+          v[r][2 * h] = d2.x;
+          v[r][2 * h + 1] = d2.y;
+        }
+    }
     F g = f;
     double in3[3] = {0.0, 0.0, 0.0};
     if (IN != IN_NONE) {

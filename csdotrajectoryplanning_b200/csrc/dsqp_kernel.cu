@@ -721,12 +721,6 @@ template <int MODE, bool AFTER_SOLVE = false>
 __device__ __forceinline__ void step_rows(Ctx &c, const csdo_params &P, bool store_dy, double rho_old,
                                           RowRegs *RR = nullptr) {
   DBG_INIT();
-#ifdef CSDO_NO_PLANE_AHEAD
-  constexpr bool kAhead = false;
-#else
-  constexpr bool kAhead = (MODE == 2);   // the hot pass: the first plane's record is loaded ahead (PlaneAhead)
-#endif
-  if (kAhead) planes_prefetch_first(c);
   StepF<MODE> sf;
   sf.alpha = P.alpha; sf.rho = c.rho; sf.rho_old = rho_old;
   sf.store_dy = store_dy; sf.dy_base = c.dy() + c.t(); sf.dy_stride = c.NT();
