@@ -481,6 +481,21 @@ def main():
         tb, rb = cpu_port_run(p, sample, cores, linsys=1)
         cpu_banded = {"value": int(rb.n_qp.sum()) / tb, "unit": UNIT, "cores": cores, "kind": "port",
                       "sample": f"same sample, reduced banded system instead of the KKT LDL^T (linsys=1), {tb:.1f} s"}
+        # the yardstick for the per-agent differences above: the oracle against ITSELF with the other linear
+        # solver (KKT LDL^T vs reduced banded system, both CPU, both exact solves differing at rounding level)
+        dself = np.zeros(len(a_idx))
+        pos = 0
+        for j, a in enumerate(a_idx):
+            n6 = 6 * int(batch.agent_off[a + 1] - batch.agent_off[a])
+            dself[j] = np.abs(rb.traj[pos:pos + n6] - r.traj[pos:pos + n6]).max(); pos += n6
+        parity["oracle_kkt_vs_oracle_banded"] = {
+            "what": "the same CPU oracle with its two linear-system paths on the same sample: how far rounding-level "
+                    "differences alone move the result of this algorithm",
+            "status_equal": bool(np.array_equal(rb.status, r.status)),
+            "admm_iters_equal": bool(np.array_equal(rb.admm_iters, r.admm_iters)),
+            "agents_differing_in_admm_iters": int((rb.admm_iters != r.admm_iters).sum()),
+            "max_abs_traj": float(dself.max()), "median_abs_traj": float(np.median(dself)),
+            "agents_within_1e-6": int((dself < 1e-6).sum()), "agents_within_1e-3": int((dself < 1e-3).sum())}
     latency = None
     if world == 1 and not args.no_cpu_baseline:
         latency = latency_block(p, DsqpSolver, local_rank)
