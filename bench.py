@@ -44,6 +44,9 @@ WORKLOADS = {
     "map50": (600, "BASELINE configs[1] shape: map50by50 sweep, agents 5/10/15/20/25 x {empty, 25 obstacles}"),
     "map100_a100": (60, "BASELINE configs[2] shape: map100by100 / agents100 / obstacle (100 agents, 50 obstacles)"),
     "room": (300, "BASELINE configs[3] shape: room maps 100x100, agents 10..50, 130..298 wall discs of r = 0.5"),
+    "real": (455, "REAL benchmark geometry: the 455 scenarios of benchmark/{map50by50,map100by100,room} that the stand-in "
+                  "planner (tools/coarse_planner.cpp) routes completely (tests/golden/real_scenarios.npz: real maps, "
+                  "obstacles, starts and goals; coarse plans by the stand-in, x0_bar by InterpolateInitalGuess)"),
 }
 C5_FULL = 4096   # BASELINE configs[4] names 4096 concurrent instances
 
@@ -53,10 +56,14 @@ def workload_string(name: str, total: int) -> str:
     if name == "c5" and total != C5_FULL:
         s += (f"; configs[4] names {C5_FULL} instances -- {total} keeps one step within seconds "
               f"(--instances {C5_FULL} runs the full size)")
-    return s + "; synthetic priority-style plans"
+    return s + ("" if name == "real" else "; synthetic priority-style plans")
 
 
 def build_instances(name: str, total: int, rank: int, world: int, params):
+    if name == "real":     # instance i = scenario i mod 455 of the committed fixture
+        from csdotrajectoryplanning_b200.driver import instances_from_coarse_plans
+        fix = os.path.join(ROOT, "tests", "golden", "real_scenarios.npz")
+        return instances_from_coarse_plans(fix, params, select=[i % 455 for i in range(total)][rank::world])
     from tools import synth
     jobs = synth.workload_jobs(name, total)[rank::world]
     return synth.synth_jobs(jobs, params)
@@ -187,7 +194,8 @@ def run_reference(args, rank: int, world: int):
             f"(OpenMP over agents; the reference itself runs the agents sequentially on one core)")
     line = {"metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "real benchmark scenarios, stand-in coarse plans" if args.workload == "real" else "synthetic",
             "refine_ms_per_instance": 1e3 * t_tot / args.steps / len(chosen),
             "config": config_dict(args, total), "details": {"sample": desc},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
@@ -504,7 +512,8 @@ def main():
            if agents_mode else f"instance-sharded x{world} (rank r refines instances r, r+{world}, ...), no data-path collective")
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "real benchmark scenarios, stand-in coarse plans" if args.workload == "real" else "synthetic",
             "refine_ms_per_instance": 1e3 * t_dev / args.steps / max(tot_inst, 1),   # whole job: step time / all instances
             "config": config_dict(args, total),
             "details": {"instances_total": tot_inst, "agents_total": tot_agents, "qp_per_step_total": tot_qp // args.steps,
