@@ -27,6 +27,10 @@ struct csdo_handle {
   std::string err;
   int num_sms = 0, smem_limit = 0, smem_limit_sm = 0;
   DevBuf scratch, queue, step_cnt, pass_buf, tile_sum;
+  // horizon buckets of one refine (run_refine_bucketed): the grouped processing order; `queue` holds one
+  // control block of 2048 B per bucket (the buckets run one after the other and share everything else)
+  DevBuf order_buf;
+  int buckets_used = 1;
   std::vector<DevBuf> stage;  // staging buffers of the host-pointer entry points
   csdo_launch_info last{};
 };
@@ -44,6 +48,8 @@ struct DeviceGuard {
 };
 
 constexpr int PL_BYTES_PER_PLANE = 6 * 4 * 8;
+constexpr int kMaxBuckets = 8;
+constexpr int kQueueCtrlBytes = 2048;   // one work-queue control block
 
 bool set_err(csdo_handle *h, const char *what, cudaError_t e) {
   if (e == cudaSuccess) return false;
@@ -181,7 +187,10 @@ DevBatch as_dev(const csdo_batch *in) {
 }
 
 // configure + enqueue the refine kernels on device-resident data
-int run_refine(csdo_handle *h, const DevBatch &B, const DevOut &O, int max_nt, int max_k, cudaStream_t stream) {
+// bucket: which queue control block the launch uses (csdo_sync reads every block's error flag);
+// init_outputs / aggregate: see launch_refine
+int run_refine(csdo_handle *h, const DevBatch &B, const DevOut &O, int max_nt, int max_k, cudaStream_t stream,
+               int bucket = 0, bool init_outputs = true, bool aggregate = true, bool record = true) {
   if (B.n_agents == 0) return CSDO_OK;
   if (max_nt < 3) { h->err = "horizon < 3"; return CSDO_ERR_INVALID; }
   if (max_nt > kMaxThreads) { h->err = "horizon exceeds 512 steps"; return CSDO_ERR_UNSUPPORTED; }
@@ -233,17 +242,115 @@ int run_refine(csdo_handle *h, const DevBatch &B, const DevOut &O, int max_nt, i
   const int n_work = (B.n_active > 0 && B.agent_order) ? B.n_active : B.n_agents;
   const int grid = std::min(n_work, h->num_sms * occ);
   int rc;
-  if ((rc = ensure(h, h->scratch, (size_t)grid * LY.slot_doubles * sizeof(double)))) return rc;
-  if ((rc = ensure(h, h->queue, 2048))) return rc;
-  if ((rc = ensure(h, h->pass_buf, refine_queue_bytes(B.n_agents, h->P)))) return rc;
+  DevBuf &scratch = h->scratch;
+  DevBuf &items = h->pass_buf;
+  if ((rc = ensure(h, scratch, (size_t)grid * LY.slot_doubles * sizeof(double)))) return rc;
+  if ((rc = ensure(h, h->queue, (size_t)kMaxBuckets * kQueueCtrlBytes))) return rc;
+  if ((rc = ensure(h, items, refine_queue_bytes(n_work, h->P)))) return rc;
   int launches = 0;
+  int *ctrl = reinterpret_cast<int *>(static_cast<char *>(h->queue.p) + (size_t)bucket * kQueueCtrlBytes);
   if (set_err(h, "launch_refine",
-              launch_refine(B, O, h->P, LY, static_cast<double *>(h->scratch.p), static_cast<int *>(h->queue.p),
-                            h->pass_buf.p, grid, block, lean, stream, &launches)))
+              launch_refine(B, O, h->P, LY, static_cast<double *>(scratch.p), ctrl, items.p, grid, block, lean, stream,
+                            &launches, init_outputs, aggregate)))
     return CSDO_ERR_CUDA;
-  h->last.launches = launches;
-  h->last.grid = grid; h->last.block = block; h->last.smem_bytes = LY.smem_doubles * 8;
-  h->last.tier = LY.tier; h->last.ctas_per_sm = occ;
+  if (record) {
+    h->last.launches = launches;
+    h->last.grid = grid; h->last.block = block; h->last.smem_bytes = LY.smem_doubles * 8;
+    h->last.tier = LY.tier; h->last.ctas_per_sm = occ;
+    h->buckets_used = 1;
+  } else {
+    h->last.launches += launches;
+  }
+  return CSDO_OK;
+}
+
+// ---- horizon buckets -------------------------------------------------------------------------------------
+// One launch sizes its CTAs (threads, shared memory, solver variant) for the LONGEST horizon of what it is
+// given: in a batch with mixed horizons (a real map set: 40 ... 250 steps) every short agent would run in the
+// long agents' launch shape -- 1 CTA/SM instead of 3-4.  The agents are therefore grouped by horizon class
+// (block size: 64, 96, 128, ... in steps of 32) and each class is refined by its own launch, longest horizons
+// first, one after the other on the caller's stream (forking them onto separate streams measured the same: a
+// long-horizon CTA leaves no shared memory for a second kernel's CTA on its SM).  Classes with fewer
+// than ~4 agents per SM are merged into the next larger class of the same solver family (<= 96 steps: one-warp
+// solver, above: CTA-wide solver; inside a family the arithmetic does not depend on the launch shape).
+struct Bucket {
+  int nt;      // longest horizon in the bucket
+  int count, offset;   // segment of the grouped order
+};
+
+int horizon_class(int nt) { return std::max(64, (nt + 31) & ~31); }
+
+// order: the agents to refine, in processing order (longest first); agent_nt: horizon of every agent of the batch.
+// Returns the order grouped by bucket (largest horizons first) and the buckets.
+void plan_buckets(const std::vector<int> &order, const std::vector<int> &agent_nt, int min_count,
+                  std::vector<int> &grouped, std::vector<Bucket> &buckets) {
+  const int n_cls = kMaxThreads / 32 + 1;
+  std::vector<int> cnt(n_cls, 0), ntmax(n_cls, 0), target(n_cls);
+  for (int a : order) {
+    const int c = horizon_class(agent_nt[a]) / 32;
+    cnt[c]++; ntmax[c] = std::max(ntmax[c], agent_nt[a]);
+  }
+  for (int c = 0; c < n_cls; ++c) target[c] = c;
+  auto family = [](int c) { return 32 * c <= 96 ? 0 : 1; };
+  auto next_used = [&](int c) { for (int d = c + 1; d < n_cls; ++d) if (cnt[d]) return d; return -1; };
+  auto merge_up = [&](int c, int d) { cnt[d] += cnt[c]; ntmax[d] = std::max(ntmax[d], ntmax[c]); cnt[c] = 0; target[c] = d; };
+  for (int c = 0; c < n_cls; ++c) {   // small classes move up inside their family
+    if (!cnt[c] || cnt[c] >= min_count) continue;
+    const int d = next_used(c);
+    if (d >= 0 && family(d) == family(c)) merge_up(c, d);
+  }
+  for (;;) {                          // at most kMaxBuckets launches: fold the smallest class into its upper neighbour
+    int used = 0, best = -1;
+    for (int c = 0; c < n_cls; ++c) if (cnt[c]) { ++used; if (next_used(c) >= 0 && (best < 0 || cnt[c] < cnt[best])) best = c; }
+    if (used <= kMaxBuckets || best < 0) break;
+    merge_up(best, next_used(best));
+  }
+  auto final_of = [&](int c) { while (target[c] != c) c = target[c]; return c; };
+  buckets.clear();
+  std::vector<int> slot(n_cls, -1);
+  for (int c = n_cls - 1; c >= 0; --c)
+    if (cnt[c]) { slot[c] = (int)buckets.size(); buckets.push_back({ntmax[c], cnt[c], 0}); }
+  int off = 0;
+  for (auto &b : buckets) { b.offset = off; off += b.count; }
+  grouped.resize(order.size());
+  std::vector<int> fill(buckets.size(), 0);
+  for (int a : order) {
+    const int b = slot[final_of(horizon_class(agent_nt[a]) / 32)];
+    grouped[buckets[b].offset + fill[b]++] = a;
+  }
+}
+
+// Refine `order` (host copy of the processing order) bucket by bucket.  B.agent_order / n_active are replaced.
+int run_refine_bucketed(csdo_handle *h, DevBatch B, const DevOut &O, const std::vector<int> &order,
+                        const std::vector<int> &agent_nt, int max_k, cudaStream_t stream) {
+  if (order.empty()) return CSDO_OK;
+  std::vector<int> grouped;
+  std::vector<Bucket> buckets;
+  const char *off = getenv("CSDO_NO_BUCKETS");   // developer knob: one launch shaped for the longest horizon
+  if (off && atoi(off)) {
+    int nt = 0;
+    for (int a : order) nt = std::max(nt, agent_nt[a]);
+    grouped = order;
+    buckets.push_back({nt, (int)order.size(), 0});
+  } else {
+    const char *mc = getenv("CSDO_BUCKET_MIN");   // developer knob: smallest class that keeps its own launch
+    plan_buckets(order, agent_nt, mc ? std::max(1, atoi(mc)) : 4 * h->num_sms, grouped, buckets);
+  }
+  int rc;
+  if ((rc = ensure(h, h->order_buf, grouped.size() * sizeof(int)))) return rc;
+  if (set_err(h, "cudaMemcpyAsync H2D", cudaMemcpyAsync(h->order_buf.p, grouped.data(), grouped.size() * sizeof(int),
+                                                        cudaMemcpyHostToDevice, stream)))
+    return CSDO_ERR_CUDA;
+  if (set_err(h, "init_outputs", launch_init_outputs(B, O, stream))) return CSDO_ERR_CUDA;
+  const int nb = (int)buckets.size();
+  for (int b = 0; b < nb; ++b) {
+    B.agent_order = static_cast<const int *>(h->order_buf.p) + buckets[b].offset;
+    B.n_active = buckets[b].count;
+    if ((rc = run_refine(h, B, O, buckets[b].nt, max_k, stream, b, false, false, b == 0))) return rc;
+  }
+  h->buckets_used = nb;
+  if (set_err(h, "aggregate_status", launch_aggregate_status(B, O, stream))) return CSDO_ERR_CUDA;
+  h->last.launches += 2;
   return CSDO_OK;
 }
 
@@ -308,6 +415,7 @@ void csdo_destroy(csdo_handle *h) {
   if (h->step_cnt.p) cudaFree(h->step_cnt.p);
   if (h->pass_buf.p) cudaFree(h->pass_buf.p);
   if (h->tile_sum.p) cudaFree(h->tile_sum.p);
+  if (h->order_buf.p) cudaFree(h->order_buf.p);
   cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -340,6 +448,52 @@ int csdo_refine_device(csdo_handle *h, const csdo_batch *in, csdo_result *out, i
   return run_refine(h, B, O, max_nt, max_planes, s);
 }
 
+int csdo_refine_device_hinted(csdo_handle *h, const csdo_batch *in, csdo_result *out, int max_planes,
+                              const int32_t *host_inst_nt, const int32_t *host_inst_agent_ptr,
+                              const int32_t *host_order, int32_t n_order, void *cuda_stream) {
+  if (!h || !in || !out || !host_inst_nt || !host_inst_agent_ptr || n_order < 0 || (n_order > 0 && !host_order)) return CSDO_ERR_INVALID;
+  if (!out->traj || !out->corridors || !out->status || !out->sqp_iters || !out->n_qp || !out->admm_iters ||
+      !out->n_factor || !out->objective || !out->inst_status || !out->inst_static_legal) {
+    h->err = "csdo_refine_device_hinted: every csdo_result array is required"; return CSDO_ERR_INVALID;
+  }
+  if (in->n_agents > 0 && (!in->inst_agent_ptr || !in->inst_nt || !in->inst_dims || !in->obs_ptr || !in->agent_off ||
+                           !in->guess || !in->plane_ptr)) {
+    h->err = "null array in batch"; return CSDO_ERR_INVALID;
+  }
+  if (in->n_agents == 0) return CSDO_OK;
+  if (host_inst_agent_ptr[0] != 0 || host_inst_agent_ptr[in->n_inst] != in->n_agents) {
+    h->err = "host_inst_agent_ptr does not cover the agents"; return CSDO_ERR_INVALID;
+  }
+  std::vector<int> agent_nt(in->n_agents);
+  for (int i = 0; i < in->n_inst; ++i) {
+    const int nt = host_inst_nt[i];
+    if (nt < 3) { h->err = "horizon < 3"; return CSDO_ERR_INVALID; }
+    if (nt > kMaxThreads) { h->err = "horizon exceeds 512 steps"; return CSDO_ERR_UNSUPPORTED; }
+    if (host_inst_agent_ptr[i + 1] < host_inst_agent_ptr[i]) { h->err = "host_inst_agent_ptr not monotonic"; return CSDO_ERR_INVALID; }
+    for (int a = host_inst_agent_ptr[i]; a < host_inst_agent_ptr[i + 1]; ++a) agent_nt[a] = nt;
+  }
+  std::vector<int> order;
+  if (n_order > 0) {
+    order.assign(host_order, host_order + n_order);
+    std::vector<char> seen((size_t)in->n_agents, 0);
+    for (int v : order) {
+      if (v < 0 || v >= in->n_agents || seen[v]) { h->err = "host_order is not a list of distinct agent ids"; return CSDO_ERR_INVALID; }
+      seen[v] = 1;
+    }
+  } else {   // every agent, longest horizon first
+    order.resize(in->n_agents);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return agent_nt[x] > agent_nt[y]; });
+  }
+  DeviceGuard guard(h->device);
+  DevBatch B = as_dev(in);
+  DevOut O{out->traj, out->corridors, out->status, out->sqp_iters, out->n_qp, out->admm_iters,
+           out->n_factor, out->objective, out->inst_status, out->inst_static_legal};
+  cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->stream;
+  h->last_stream = s;
+  return run_refine_bucketed(h, B, O, order, agent_nt, max_planes, s);
+}
+
 int csdo_aggregate_status_device(csdo_handle *h, const csdo_batch *in, csdo_result *out, void *cuda_stream) {
   if (!h || !in || !out || !out->status || !out->inst_status || !in->inst_agent_ptr) return CSDO_ERR_INVALID;
   DeviceGuard guard(h->device);
@@ -359,8 +513,13 @@ int csdo_sync(csdo_handle *h) {
   if (set_err(h, "csdo_sync", cudaStreamSynchronize(s))) return CSDO_ERR_CUDA;
   if (!h->queue.p) return CSDO_OK;
   int qerr = 0;
-  if (set_err(h, "csdo_sync", cudaMemcpy(&qerr, static_cast<int *>(h->queue.p) + kQError, sizeof(int), cudaMemcpyDeviceToHost)))
-    return CSDO_ERR_CUDA;
+  for (int b = 0; b < h->buckets_used && h->queue.cap >= (size_t)(b + 1) * kQueueCtrlBytes; ++b) {
+    int e = 0;
+    if (set_err(h, "csdo_sync", cudaMemcpy(&e, reinterpret_cast<int *>(static_cast<char *>(h->queue.p) + (size_t)b * kQueueCtrlBytes) + kQError,
+                                           sizeof(int), cudaMemcpyDeviceToHost)))
+      return CSDO_ERR_CUDA;
+    if (e) qerr = (qerr == 2 || e == 2) ? 2 : e;
+  }
   if (qerr == 2) { h->err = "refine: an agent has more planes than max_planes"; return CSDO_ERR_INVALID; }
   if (qerr) { h->err = "refine: work queue stalled"; return CSDO_ERR_CUDA; }
   return CSDO_OK;
@@ -386,8 +545,9 @@ int csdo_refine(csdo_handle *h, const csdo_batch *in, csdo_result *out) {
       cost[a] = 13 * (in->agent_off[a + 1] - in->agent_off[a]) + 4 * (int64_t)(in->plane_ptr[a + 1] - in->plane_ptr[a]);
     std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cost[x] > cost[y]; });
   }
-  if ((rc = upload(h, 10, order.data(), order.size(), &B.agent_order))) return rc;
-  B.n_active = in->agent_order ? in->n_active : 0;
+  order.resize(n_listed);
+  std::vector<int> agent_nt(in->n_agents);
+  for (int a = 0; a < in->n_agents; ++a) agent_nt[a] = (int)(in->agent_off[a + 1] - in->agent_off[a]);
   DevOut O;
   const size_t A = in->n_agents, I = in->n_inst;
   if ((rc = devalloc(h, 11, 6 * (size_t)m.steps, &O.traj))) return rc;
@@ -397,7 +557,7 @@ int csdo_refine(csdo_handle *h, const csdo_batch *in, csdo_result *out) {
   O.status = ints; O.sqp_iters = ints + A; O.n_qp = ints + 2 * A; O.admm_iters = ints + 3 * A;
   O.n_factor = ints + 4 * A; O.inst_status = ints + 5 * A; O.inst_static_legal = ints + 5 * A + I;
   if ((rc = devalloc(h, 14, A, &O.objective))) return rc;
-  if ((rc = run_refine(h, B, O, m.max_nt, m.max_k, h->stream))) return rc;
+  if ((rc = run_refine_bucketed(h, B, O, order, agent_nt, m.max_k, h->stream))) return rc;
   if ((rc = download(h, out->traj, O.traj, 6 * (size_t)m.steps))) return rc;
   if ((rc = download(h, out->corridors, O.corridors, 8 * (size_t)m.steps))) return rc;
   if ((rc = download(h, out->status, O.status, A))) return rc;

@@ -1517,9 +1517,15 @@ size_t refine_queue_bytes(int n_agents, const csdo_params &P) {
   return ((size_t)n_agents * visits + 64) * sizeof(int);
 }
 
+cudaError_t launch_init_outputs(const DevBatch &B, const DevOut &O, cudaStream_t stream) {
+  const int fb = 256;
+  fill_int_kernel<<<(B.n_inst + fb - 1) / fb, fb, 0, stream>>>(O.inst_static_legal, B.n_inst, 1);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_refine(const DevBatch &B, const DevOut &O, const csdo_params &P, const Layout &LY,
                           double *scratch, int *queue, void *queue_items, int grid, int block, bool lean,
-                          cudaStream_t stream, int *n_launches) {
+                          cudaStream_t stream, int *n_launches, bool init_outputs, bool aggregate) {
   const int smem = LY.smem_doubles * 8;
   RefineKernel kern = pick_kernel(block, lean);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -1527,15 +1533,15 @@ cudaError_t launch_refine(const DevBatch &B, const DevOut &O, const csdo_params 
   if (const char *co = getenv("CSDO_CARVEOUT"))  // developer knob: shared-memory carve-out in percent
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(co));
   const int fb = 256, n = (B.n_active > 0 && B.agent_order) ? B.n_active : B.n_agents;
-  QueueState qs{static_cast<int *>(queue_items), (int)(refine_queue_bytes(B.n_agents, P) / sizeof(int))};
+  QueueState qs{static_cast<int *>(queue_items), (int)(refine_queue_bytes(n, P) / sizeof(int))};
   e = cudaMemsetAsync(queue, 0, 2048, stream);
   if (e != cudaSuccess) return e;
-  fill_int_kernel<<<(B.n_inst + fb - 1) / fb, fb, 0, stream>>>(O.inst_static_legal, B.n_inst, 1);
+  if (init_outputs) fill_int_kernel<<<(B.n_inst + fb - 1) / fb, fb, 0, stream>>>(O.inst_static_legal, B.n_inst, 1);
   queue_init_kernel<<<(qs.cap + fb - 1) / fb, fb, 0, stream>>>(n, B.n_agents, B.agent_order, qs.items, qs.cap, queue,
                                                                O.sqp_iters);
   kern<<<grid, block, smem, stream>>>(B, O, P, LY, scratch, queue, qs);
-  aggregate_status_kernel<<<(B.n_inst + fb - 1) / fb, fb, 0, stream>>>(B, O);
-  if (n_launches) *n_launches = 4;
+  if (aggregate) aggregate_status_kernel<<<(B.n_inst + fb - 1) / fb, fb, 0, stream>>>(B, O);
+  if (n_launches) *n_launches = 2 + (init_outputs ? 1 : 0) + (aggregate ? 1 : 0);
   return cudaGetLastError();
 }
 

@@ -66,9 +66,12 @@ void read_debug_counters(unsigned long long *out16);
 
 // queue_items: refine_queue_bytes() of device memory
 size_t refine_queue_bytes(int n_agents, const csdo_params &P);
+// init_outputs: set inst_static_legal to 1 first; aggregate: run the status aggregation afterwards (a bucketed
+// refine does both once, around its per-bucket launches)
 cudaError_t launch_refine(const DevBatch &B, const DevOut &O, const csdo_params &P, const Layout &LY,
                           double *scratch, int *queue, void *queue_items, int grid, int block, bool lean,
-                          cudaStream_t stream, int *n_launches);
+                          cudaStream_t stream, int *n_launches, bool init_outputs = true, bool aggregate = true);
+cudaError_t launch_init_outputs(const DevBatch &B, const DevOut &O, cudaStream_t stream);
 cudaError_t launch_aggregate_status(const DevBatch &B, const DevOut &O, cudaStream_t stream);
 cudaError_t launch_corridors(const DevBatch &B, const csdo_params &P, int double_centres, double *corridors,
                              int *box_status, int *inst_static_legal, cudaStream_t stream);

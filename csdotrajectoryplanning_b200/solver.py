@@ -62,10 +62,27 @@ class DsqpSolver:
         return res
 
     # -- whole refine, tensors resident in HBM (csdo_refine_device) --------
-    def refine_device(self, dbatch: "DeviceBatch", dres: "DeviceResult", stream_ptr: int = 0) -> None:
-        self._check(self._lib.csdo_refine_device(self._h, C.byref(dbatch.c), C.byref(dres.c),
-                                                 dbatch.max_nt, dbatch.max_planes,
-                                                 C.c_void_p(stream_ptr) if stream_ptr else None))
+    def refine_device(self, dbatch: "DeviceBatch", dres: "DeviceResult", stream_ptr: int = 0,
+                      by_horizon: bool = True) -> None:
+        """Refine a device-resident batch.  by_horizon (default): csdo_refine_device_hinted -- the host copies of
+        inst_nt / inst_agent_ptr that the DeviceBatch keeps let the library launch one kernel per horizon class;
+        False: csdo_refine_device, one launch shaped for the longest horizon of the batch."""
+        sp = C.c_void_p(stream_ptr) if stream_ptr else None
+        if not by_horizon:
+            self._check(self._lib.csdo_refine_device(self._h, C.byref(dbatch.c), C.byref(dres.c),
+                                                     dbatch.max_nt, dbatch.max_planes, sp))
+            return
+        b = dbatch.host
+        nt = np.ascontiguousarray(b.inst_nt, np.int32)
+        ptr = np.ascontiguousarray(b.inst_agent_ptr, np.int32)
+        ids = getattr(dbatch, "active_ids", None)
+        order, n_order = None, 0
+        if ids is not None:      # agent-partitioned mode: this rank's agents, longest horizon first
+            a_nt = b.agent_nt()[ids]
+            o = np.ascontiguousarray(ids[np.argsort(-a_nt, kind="stable")], np.int32)
+            order, n_order = o.ctypes.data, int(o.shape[0])
+        self._check(self._lib.csdo_refine_device_hinted(self._h, C.byref(dbatch.c), C.byref(dres.c), dbatch.max_planes,
+                                                        nt.ctypes.data, ptr.ctypes.data, order, n_order, sp))
 
     def aggregate_status_device(self, dbatch: "DeviceBatch", dres: "DeviceResult", stream_ptr: int = 0) -> None:
         """SolverDSQP's status aggregation over all agents (after the all-gather of the agent-partitioned mode)."""

@@ -174,6 +174,24 @@ int csdo_refine(csdo_handle *h, const csdo_batch *in, csdo_result *out);
 int csdo_refine_device(csdo_handle *h, const csdo_batch *in, csdo_result *out,
                        int max_nt, int max_planes, void *cuda_stream);
 
+/* csdo_refine_device with HOST copies of the small per-instance arrays, so that
+ * the library can group the agents by horizon without reading device memory:
+ * one launch per horizon class (block size 64, 96, 128, ... steps), longest
+ * first, all on `cuda_stream` -- in a batch of mixed horizons the short agents
+ * then run in their own launch shape (3-4 CTAs per SM) instead of the longest
+ * agent's.  csdo_refine (host
+ * buffers) always works this way.  host_inst_nt [n_inst], host_inst_agent_ptr
+ * [n_inst+1]: host copies of in->inst_nt / in->inst_agent_ptr; host_order
+ * [n_order]: the agents to refine in processing order (NULL / 0: all agents,
+ * longest horizon first); in->agent_order / in->n_active are ignored.  Returns
+ * without synchronizing.  Results are those of csdo_refine_device up to the
+ * rounding of the solver variant a horizon class selects. */
+int csdo_refine_device_hinted(csdo_handle *h, const csdo_batch *in, csdo_result *out,
+                              int max_planes, const int32_t *host_inst_nt,
+                              const int32_t *host_inst_agent_ptr,
+                              const int32_t *host_order, int32_t n_order,
+                              void *cuda_stream);
+
 /* SolverDSQP's status aggregation (dsqp_solver.cc:1224-1243) over ALL agents of
  * every instance from out->status into out->inst_status (DEVICE pointers).
  * csdo_refine* run it themselves; it is exported for the agent-partitioned

@@ -21,6 +21,8 @@ if name.startswith("c5"):
 elif name == "map50":
     from csdotrajectoryplanning_b200.scenario import MAP50_SWEEP, synthetic_batch
     inst = synthetic_batch(MAP50_SWEEP, per, seed=1234, params=p)
+elif name == "real":
+    inst = bench.build_instances("real", per, 0, 1, p)
 else:
     raise SystemExit("unknown workload")
 S = DsqpSolver(p)
