@@ -49,6 +49,7 @@ struct DeviceGuard {
 
 constexpr int PL_BYTES_PER_PLANE = 6 * 4 * 8;
 constexpr int kMaxBuckets = 8;
+constexpr int kOneWarpMaxNTHost = 96;   // = kOneWarpMaxNT of dsqp_device.cuh (block sizes that use the one-warp solver)
 constexpr int kQueueCtrlBytes = 2048;   // one work-queue control block
 
 bool set_err(csdo_handle *h, const char *what, cudaError_t e) {
@@ -186,6 +187,15 @@ DevBatch as_dev(const csdo_batch *in) {
   return B;
 }
 
+// stride / footprint class of a horizon: multiples of 32 up to the one-warp solver's limit, of 16 above
+// Multiples of 32.  (Developer knob CSDO_NT_GRAN=16: strides in steps of 16 above 96 steps, so that horizons
+// 129..144 fit two CTAs per SM (108 KB at NT = 144) -- measured slower on the real map set, 90.8 k vs 94.5 k QP/s:
+// the extra classes are small and end up merged into longer ones.)
+int launch_nt(int nt) {
+  static const int gran = getenv("CSDO_NT_GRAN") ? std::max(16, atoi(getenv("CSDO_NT_GRAN")) & ~15) : 32;
+  return nt <= kOneWarpMaxNTHost ? std::max(64, (nt + 31) & ~31) : ((nt + gran - 1) / gran * gran);
+}
+
 // configure + enqueue the refine kernels on device-resident data
 // bucket: which queue control block the launch uses (csdo_sync reads every block's error flag);
 // init_outputs / aggregate: see launch_refine
@@ -194,12 +204,13 @@ int run_refine(csdo_handle *h, const DevBatch &B, const DevOut &O, int max_nt, i
   if (B.n_agents == 0) return CSDO_OK;
   if (max_nt < 3) { h->err = "horizon < 3"; return CSDO_ERR_INVALID; }
   if (max_nt > kMaxThreads) { h->err = "horizon exceeds 512 steps"; return CSDO_ERR_UNSUPPORTED; }
-  const int NT = (max_nt + 31) & ~31;
+  // NT = stride of the per-step arrays (what the shared-memory footprint scales with), block = NT rounded to warps
+  const int NT = launch_nt(max_nt);
   const int KMAX = std::max(4, (max_k + 3) & ~3);
   // placement (tier bit 0: row data / scaling / state in global scratch, bit 1: band factor in global
   // scratch): everything in shared memory when that already allows the most resident CTAs, else the
   // row arrays move out (they are read once per pass into registers); the factor moves last
-  const int block = std::max(64, NT);
+  const int block = std::max(64, (NT + 31) & ~31);
   Layout LY{};
   int occ = 0;
   bool lean = false;  // kernel variant compiled with fewer registers for one more resident CTA
@@ -278,20 +289,20 @@ struct Bucket {
   int count, offset;   // segment of the grouped order
 };
 
-int horizon_class(int nt) { return std::max(64, (nt + 31) & ~31); }
+int horizon_class(int nt) { return launch_nt(nt); }   // (defined above run_refine)
 
 // order: the agents to refine, in processing order (longest first); agent_nt: horizon of every agent of the batch.
 // Returns the order grouped by bucket (largest horizons first) and the buckets.
 void plan_buckets(const std::vector<int> &order, const std::vector<int> &agent_nt, int min_count,
                   std::vector<int> &grouped, std::vector<Bucket> &buckets) {
-  const int n_cls = kMaxThreads / 32 + 1;
+  const int n_cls = kMaxThreads / 16 + 1;
   std::vector<int> cnt(n_cls, 0), ntmax(n_cls, 0), target(n_cls);
   for (int a : order) {
-    const int c = horizon_class(agent_nt[a]) / 32;
+    const int c = horizon_class(agent_nt[a]) / 16;
     cnt[c]++; ntmax[c] = std::max(ntmax[c], agent_nt[a]);
   }
   for (int c = 0; c < n_cls; ++c) target[c] = c;
-  auto family = [](int c) { return 32 * c <= 96 ? 0 : 1; };
+  auto family = [](int c) { return 16 * c <= kOneWarpMaxNTHost ? 0 : 1; };
   auto next_used = [&](int c) { for (int d = c + 1; d < n_cls; ++d) if (cnt[d]) return d; return -1; };
   auto merge_up = [&](int c, int d) { cnt[d] += cnt[c]; ntmax[d] = std::max(ntmax[d], ntmax[c]); cnt[c] = 0; target[c] = d; };
   for (int c = 0; c < n_cls; ++c) {   // small classes move up inside their family
@@ -315,7 +326,7 @@ void plan_buckets(const std::vector<int> &order, const std::vector<int> &agent_n
   grouped.resize(order.size());
   std::vector<int> fill(buckets.size(), 0);
   for (int a : order) {
-    const int b = slot[final_of(horizon_class(agent_nt[a]) / 32)];
+    const int b = slot[final_of(horizon_class(agent_nt[a]) / 16)];
     grouped[buckets[b].offset + fill[b]++] = a;
   }
 }

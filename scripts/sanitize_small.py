@@ -12,6 +12,8 @@ if which == "short":
     inst = [synthetic_instance(7, 50.0, 4, 10, (8, 12), p), synthetic_instance(8, 50.0, 3, 0, (27, 29), p)]
 elif which == "dense":   # a small map: many inter-vehicle planes per agent (plane-major passes)
     inst = [synthetic_instance(11, 25.0, 6, 4, (9, 12), p)]
+elif which == "mid":     # horizon ~140: stride 144 in 160-thread CTAs (stride != block size), two CTAs per SM
+    inst = [synthetic_instance(12, 70.0, 3, 6, (46, 47), p)]
 elif which == "long":
     inst = [synthetic_instance(9, 60.0, 3, 6, (41, 42), p)]
 else:

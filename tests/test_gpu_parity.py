@@ -149,7 +149,7 @@ def test_ragged_batch_and_edge_sizes(oracle, params, solver):
     _assert_same_refine(ro, rg)
 
 
-@pytest.mark.parametrize("acts,na,size", [((27, 30), 6, 50.0), ((40, 42), 6, 60.0), ((50, 52), 6, 60.0),
+@pytest.mark.parametrize("acts,na,size", [((27, 30), 6, 50.0), ((40, 42), 6, 60.0), ((46, 47), 5, 70.0), ((50, 52), 6, 60.0),
                                           ((80, 80), 3, 100.0), ((135, 140), 2, 100.0)])
 def test_long_horizons_cover_every_kernel_variant(oracle, params, solver, acts, na, size):
     """Horizons 82..421: 16 partitions with the two-level separator solve, the 96/128/160/256/512-thread
