@@ -282,7 +282,10 @@ int run_refine(csdo_handle *h, const DevBatch &B, const DevOut &O, int max_nt, i
 // (block size: 64, 96, 128, ... in steps of 32) and each class is refined by its own launch, longest horizons
 // first, one after the other on the caller's stream (forking them onto separate streams measured the same: a
 // long-horizon CTA leaves no shared memory for a second kernel's CTA on its SM).  Classes with fewer
-// than ~4 agents per SM are merged into the next larger class of the same solver family (<= 96 steps: one-warp
+// than 16 agents per SM are merged into the next larger class of the same solver family -- every launch ends with
+// a tail in which the SMs run dry one by one, about as long as the longest agent's own SQP loop, and a class
+// has to be worth that: on the 455 real scenarios (6050 agents, horizons 43..205) a threshold of 4 per SM gives
+// 94.5 k QP/s, of 8 or more 120.8 k (one launch per solver family), no buckets 86.2 k (<= 96 steps: one-warp
 // solver, above: CTA-wide solver; inside a family the arithmetic does not depend on the launch shape).
 struct Bucket {
   int nt;      // longest horizon in the bucket
@@ -345,7 +348,7 @@ int run_refine_bucketed(csdo_handle *h, DevBatch B, const DevOut &O, const std::
     buckets.push_back({nt, (int)order.size(), 0});
   } else {
     const char *mc = getenv("CSDO_BUCKET_MIN");   // developer knob: smallest class that keeps its own launch
-    plan_buckets(order, agent_nt, mc ? std::max(1, atoi(mc)) : 4 * h->num_sms, grouped, buckets);
+    plan_buckets(order, agent_nt, mc ? std::max(1, atoi(mc)) : 16 * h->num_sms, grouped, buckets);
   }
   int rc;
   if ((rc = ensure(h, h->order_buf, grouped.size() * sizeof(int)))) return rc;
