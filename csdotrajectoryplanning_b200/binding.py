@@ -21,7 +21,7 @@ CSDO_OK, CSDO_ERR_INVALID, CSDO_ERR_CUDA, CSDO_ERR_UNSUPPORTED, CSDO_ERR_NOMEM =
 
 EXPORTS = [
     "csdo_default_params", "csdo_version", "csdo_create", "csdo_destroy", "csdo_last_error",
-    "csdo_refine", "csdo_refine_device", "csdo_refine_device_hinted", "csdo_last_launch", "csdo_corridors",
+    "csdo_refine", "csdo_refine_device", "csdo_refine_device_hinted", "csdo_plan_horizon_buckets", "csdo_last_launch", "csdo_corridors",
     "csdo_planes_count", "csdo_planes_fill", "csdo_planes_fill_partners", "csdo_planes_from_pairs",
     "csdo_planes_count_device", "csdo_planes_fill_device", "csdo_sync", "csdo_aggregate_status_device", "csdo_measure_fp64_peak",
 ]
@@ -61,6 +61,8 @@ def lib():
         L.csdo_refine_device_hinted.argtypes = [H, C.POINTER(CsdoBatch), C.POINTER(CsdoResult), C.c_int, C.c_void_p,
                                                 C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.csdo_refine_device_hinted.restype = C.c_int
+        L.csdo_plan_horizon_buckets.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.csdo_plan_horizon_buckets.restype = C.c_int
         L.csdo_last_launch.argtypes = [H, C.POINTER(CsdoLaunchInfo)]
         L.csdo_last_launch.restype = C.c_int
         L.csdo_corridors.argtypes = [H, C.POINTER(CsdoBatch), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]

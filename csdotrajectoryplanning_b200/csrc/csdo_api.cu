@@ -508,6 +508,22 @@ int csdo_refine_device_hinted(csdo_handle *h, const csdo_batch *in, csdo_result 
   return run_refine_bucketed(h, B, O, order, agent_nt, max_planes, s);
 }
 
+int csdo_plan_horizon_buckets(int32_t n_agents, const int32_t *agent_nt, int32_t min_count, int32_t *order_out,
+                              int32_t *bucket_nt, int32_t *bucket_count, int32_t max_buckets) {
+  if (n_agents < 0 || (n_agents > 0 && (!agent_nt || !order_out)) || !bucket_nt || !bucket_count || max_buckets < 1) return -1;
+  std::vector<int> nt(agent_nt, agent_nt + n_agents), order(n_agents), grouped;
+  for (int a = 0; a < n_agents; ++a)
+    if (nt[a] < 1 || nt[a] > kMaxThreads) return -1;
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return nt[x] > nt[y]; });
+  std::vector<Bucket> buckets;
+  if (n_agents) plan_buckets(order, nt, std::max(1, (int)min_count), grouped, buckets);
+  if ((int)buckets.size() > max_buckets) return -1;
+  for (int a = 0; a < n_agents; ++a) order_out[a] = grouped[a];
+  for (size_t b = 0; b < buckets.size(); ++b) { bucket_nt[b] = buckets[b].nt; bucket_count[b] = buckets[b].count; }
+  return (int)buckets.size();
+}
+
 int csdo_aggregate_status_device(csdo_handle *h, const csdo_batch *in, csdo_result *out, void *cuda_stream) {
   if (!h || !in || !out || !out->status || !out->inst_status || !in->inst_agent_ptr) return CSDO_ERR_INVALID;
   DeviceGuard guard(h->device);

@@ -192,6 +192,16 @@ int csdo_refine_device_hinted(csdo_handle *h, const csdo_batch *in, csdo_result 
                               const int32_t *host_order, int32_t n_order,
                               void *cuda_stream);
 
+/* The launch plan csdo_refine / csdo_refine_device_hinted use for a set of
+ * horizons (host only, no device needed): agents grouped by horizon class,
+ * longest class first; classes with fewer than min_count agents merged into the
+ * next larger class of the same solver family (<= 96 steps / above).  Writes
+ * the grouped agent ids to order_out[n_agents] and per bucket its longest
+ * horizon and agent count; returns the number of buckets (<= 8) or -1. */
+int csdo_plan_horizon_buckets(int32_t n_agents, const int32_t *agent_nt, int32_t min_count,
+                              int32_t *order_out, int32_t *bucket_nt, int32_t *bucket_count,
+                              int32_t max_buckets);
+
 /* SolverDSQP's status aggregation (dsqp_solver.cc:1224-1243) over ALL agents of
  * every instance from out->status into out->inst_status (DEVICE pointers).
  * csdo_refine* run it themselves; it is exported for the agent-partitioned
