@@ -44,7 +44,7 @@ WORKLOADS = {
     "map50": (600, "BASELINE configs[1] shape: map50by50 sweep, agents 5/10/15/20/25 x {empty, 25 obstacles}"),
     "map100_a100": (60, "BASELINE configs[2] shape: map100by100 / agents100 / obstacle (100 agents, 50 obstacles)"),
     "room": (300, "BASELINE configs[3] shape: room maps 100x100, agents 10..50, 130..298 wall discs of r = 0.5"),
-    "real": (455, "REAL benchmark geometry: the 455 scenarios of benchmark/{map50by50,map100by100,room} that the stand-in "
+    "real": (579, "REAL benchmark geometry: the 579 scenarios of benchmark/{map50by50,map100by100,room} that the stand-in "
                   "planner (tools/coarse_planner.cpp) routes completely (tests/golden/real_scenarios.npz: real maps, "
                   "obstacles, starts and goals; coarse plans by the stand-in, x0_bar by InterpolateInitalGuess)"),
 }
@@ -60,10 +60,11 @@ def workload_string(name: str, total: int) -> str:
 
 
 def build_instances(name: str, total: int, rank: int, world: int, params):
-    if name == "real":     # instance i = scenario i mod 455 of the committed fixture
+    if name == "real":     # instance i = scenario i mod N of the committed fixture
         from csdotrajectoryplanning_b200.driver import instances_from_coarse_plans
         fix = os.path.join(ROOT, "tests", "golden", "real_scenarios.npz")
-        return instances_from_coarse_plans(fix, params, select=[i % 455 for i in range(total)][rank::world])
+        n_fix = len(np.load(fix)["name"])
+        return instances_from_coarse_plans(fix, params, select=[i % n_fix for i in range(total)][rank::world])
     from tools import synth
     jobs = synth.workload_jobs(name, total)[rank::world]
     return synth.synth_jobs(jobs, params)

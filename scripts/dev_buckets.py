@@ -8,7 +8,7 @@ from csdotrajectoryplanning_b200.solver import DsqpSolver
 from tools import synth
 p = default_params()
 S = DsqpSolver(p)
-for name, inst in (("real", bench.build_instances("real", 455, 0, 1, p)), ("c5", synth.synth_batch(synth.C5_SHAPES, 8, 1234, p))):
+for name, inst in (("real", bench.build_instances("real", 579, 0, 1, p)), ("c5", synth.synth_batch(synth.C5_SHAPES, 8, 1234, p))):
     b, _ = S.planes(pack_instances(inst))
     r1 = S.refine(b); l1 = S.last_launch()
     os.environ["CSDO_NO_BUCKETS"] = "1"

@@ -23,6 +23,9 @@ FOLDERS = [("map50by50/agents5/*", 60), ("map50by50/agents10/*", 60), ("map50by5
            ("map100by100/agents25/*", 12), ("map100by100/agents100/empty", 2), ("map100by100/agents70/empty", 4)]
 
 
+RETRIES = int(os.environ.get("CSDO_PLANNER_RETRIES", "3"))   # the committed fixture: 3 (579 of 750 routed; 0: 455, 10: 580)
+
+
 def one(path):
     from csdotrajectoryplanning_b200 import default_params
     from csdotrajectoryplanning_b200.scenario import load_scenario_yaml
@@ -30,7 +33,21 @@ def one(path):
     p = default_params()
     dx, dy, obs, st, gl = load_scenario_yaml(path)
     t = time.time()
-    paths, nf = planner.plan(dx, dy, obs, st, gl, p, max_expansions=120000 if len(st) <= 25 else 40000)
+    budget = 120000 if len(st) <= 25 else 40000
+    paths, nf = planner.plan(dx, dy, obs, st, gl, p, max_expansions=budget)
+    # priority reshuffling (deterministic): agents without a path move to the front, everybody is replanned
+    perm = np.arange(len(st))
+    for _ in range(RETRIES if len(st) <= 25 else 0):
+        if not nf:
+            break
+        failed = [i for i, pth in enumerate(paths) if pth is None]
+        order = failed + [i for i in range(len(perm)) if i not in failed]
+        perm = perm[order]
+        pp, nf = planner.plan(dx, dy, obs, st[perm], gl[perm], p, max_expansions=budget)
+        paths = pp
+    if not nf and not np.array_equal(perm, np.arange(len(st))):    # back to the scenario's agent numbering
+        inv = np.argsort(perm)
+        paths = [paths[inv[a]] for a in range(len(st))]
     return path, dx, dy, obs, st, gl, paths, nf, time.time() - t
 
 
@@ -55,7 +72,7 @@ def main():
                 out["states"].append(s); out["actions"].append(np.concatenate([a, [-1]]).astype(np.int8))
                 out["st_ptr"].append(out["st_ptr"][-1] + len(s))
     print("routed completely:", routed, "of", tried)
-    np.savez_compressed(os.path.join(HERE, "real_scenarios.npz"),
+    np.savez_compressed(os.environ.get("CSDO_FIXTURE_OUT", os.path.join(HERE, "real_scenarios.npz")),
                         name=np.asarray(out["name"]), dims=np.asarray(out["dims"]), obs_ptr=np.asarray(out["obs_ptr"], np.int32),
                         obs=np.concatenate(out["obs"]) if out["obs"] else np.zeros((0, 3)),
                         agent_ptr=np.asarray(out["agent_ptr"], np.int32), starts=np.concatenate(out["starts"]),

@@ -1,7 +1,8 @@
-"""Real benchmark geometry: tests/golden/real_scenarios.npz holds 455 of the
+"""Real benchmark geometry: tests/golden/real_scenarios.npz holds 579 of the
 reference's own benchmark scenarios (map50by50 agents 5..25 empty/obstacle, room agents 10/20, map100by100
 agents25: real map sizes, obstacle lists, starts, goals) together with coarse plans from the stand-in
-prioritized planner (tools/coarse_planner.cpp; the reference's PBS + Hybrid A* cannot be built offline).
+prioritized planner (tools/coarse_planner.cpp with up to 3 rounds of priority reshuffling; the reference's PBS +
+Hybrid A* cannot be built offline).
 CPU: the fixture against the YAML files (where /root/reference exists), the YAML quirks, the host chain.
 GPU: the whole set as ONE batch -- success rate, collision verdict, and a sample against the oracle."""
 import glob
@@ -96,17 +97,18 @@ def test_gpu_dummy_obstacles_match_oracle(oracle, params, solver):
 
 @pytest.mark.gpu
 def test_gpu_real_benchmark_set_one_batch(oracle, params, solver, tmp_path):
-    """All 455 routed real scenarios (6050 agents) as one batch: success rule of analysis_result.py, collision
+    """All 579 routed real scenarios (8640 agents) as one batch: success rule of analysis_result.py, collision
     verdict of collision_detection.py on the 3-decimal output, and the oracle on a sample of the same batch."""
     inst = instances_from_coarse_plans(FIX, params)
-    assert len(inst) == 455 and sum(i.n_agents for i in inst) == 6050
+    n = len(inst)
+    assert n == 579 and sum(i.n_agents for i in inst) == 8640
     rep = run_mapset(inst, solver, out_dir=str(tmp_path / "out"), check_collisions=True)
-    assert len(rep.files) == 455 and os.path.getsize(rep.files[0]) > 1000
+    assert len(rep.files) == n and os.path.getsize(rep.files[0]) > 1000
     s = rep.summary()
     assert s["success_rate"] >= 0.95, s
     assert s["collision_free"] >= 0.9, s
     # oracle on every 12th instance: identical statuses / verdicts, trajectories close on the bulk
-    sel = list(range(0, 455, 12))
+    sel = list(range(0, n, 12))
     sub = [inst[i] for i in sel]
     for ins in sub:
         ins.plane_t, ins.plane_abc, _ = oracle.instance_planes(params, ins.guess)
