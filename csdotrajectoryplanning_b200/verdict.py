@@ -81,24 +81,41 @@ def collision_circle_and_rect(circle, r) -> bool:
     return True
 
 
+# Pre-filters of verdict(): they only skip pairs for which the exact tests above provably return False.
+# Circumradius of the LF+LB by CAR_WIDTH rectangle; two rectangles whose centres are further apart than 2 R are
+# disjoint and the 4-axis SAT is exact for rectangles.  Circle vs rectangle: the third axis of
+# collision_circle_and_rect points from the circle centre c to the nearest vertex v*; every vertex w projects to
+# (w - c).axis >= |v* - c| - |w - v*| >= (D - R) - 2 R, so that axis separates as soon as D > radius + 3 R.
+_R_CIRC = math.hypot((LF + LB) / 2, CAR_WIDTH / 2)
+
+
 def verdict(trajs: List[np.ndarray], obstacles: np.ndarray) -> Tuple[List[Tuple[int, int, int]], List[Tuple[int, int, int]]]:
     """trajs: per agent (>=3, Nt) arrays (x, y, yaw rows); obstacles (No, 2|3).
     -> (inter collisions [(t, i, j)], static collisions [(t, agent, obstacle index)])."""
     na = len(trajs)
     nt = max(t.shape[1] for t in trajs)
+    obs = np.asarray(obstacles, np.float64)
+    obs = obs.reshape(-1, obs.shape[-1] if obs.size else 3)
+    rad = obs[:, 2] if obs.shape[1] == 3 else np.full(obs.shape[0], OBS_RADIUS_VIS)
     inter, static = [], []
     for f in range(nt):
         pos = [t[:3, min(f, t.shape[1] - 1)] for t in trajs]
         rects = [_rect(p) for p in pos]
+        cen = np.array([[r[0], r[1]] for r in rects]).reshape(na, 2)
+        d2 = ((cen[:, None, :] - cen[None, :, :]) ** 2).sum(-1)
+        close = d2 <= (2 * _R_CIRC + 1e-6) ** 2
         for ai in range(na):
-            for aj in range(ai + 1, na):
-                if collision_rect_and_rect(rects[ai], rects[aj]):
-                    inter.append((f, ai, aj))
-        for a in range(na):
-            for oi, o in enumerate(np.asarray(obstacles).reshape(-1, np.asarray(obstacles).shape[-1] if np.asarray(obstacles).size else 3)):
-                rad = o[2] if len(o) == 3 else OBS_RADIUS_VIS
-                if collision_circle_and_rect((o[0], o[1], rad), rects[a]):
-                    static.append((f, a, oi))
+            for aj in np.nonzero(close[ai, ai + 1:])[0] + ai + 1:
+                if collision_rect_and_rect(rects[ai], rects[int(aj)]):
+                    inter.append((f, ai, int(aj)))
+        if obs.shape[0]:
+            do2 = ((cen[:, None, :] - obs[None, :, :2]) ** 2).sum(-1)
+            near = do2 <= (rad[None, :] + 3 * _R_CIRC + 1e-6) ** 2
+            for a in range(na):
+                for oi in np.nonzero(near[a])[0]:
+                    o = obs[int(oi)]
+                    if collision_circle_and_rect((o[0], o[1], rad[int(oi)]), rects[a]):
+                        static.append((f, a, int(oi)))
     return inter, static
 
 

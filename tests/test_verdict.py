@@ -47,3 +47,31 @@ def test_three_decimal_format():
     tr = np.array([[1.23449, 2.0005], [0.0, -0.00049], [3.14159, -3.14159]])
     r = V.rounded_solution(tr)
     assert r.tolist() == [[1.234, 2.0], [0.0, -0.0], [3.142, -3.142]] or r[0, 1] in (2.0, 2.001)
+
+
+def test_prefilters_do_not_change_the_verdict():
+    """verdict() skips far-apart pairs before the exact tests: same lists as testing every pair."""
+    from csdotrajectoryplanning_b200 import verdict as V
+    rng = np.random.default_rng(11)
+    for trial in range(6):
+        na, nt, no = 7, 5, 9
+        size = (12.0, 25.0, 60.0)[trial % 3]                     # crowded ... sparse
+        trajs = [np.vstack([rng.uniform(0, size, (2, nt)), rng.uniform(-3.2, 3.2, (1, nt))]) for _ in range(na)]
+        obs = np.column_stack([rng.uniform(0, size, (no, 2)), rng.uniform(0.3, 2.5, no)])
+        if trial == 5:
+            obs = obs[:, :2]                                     # 2-element obstacles: radius 1
+        inter, static = V.verdict(trajs, obs)
+        bi, bs = [], []
+        for f in range(nt):
+            rects = [V._rect(t[:3, f]) for t in trajs]
+            for ai in range(na):
+                for aj in range(ai + 1, na):
+                    if V.collision_rect_and_rect(rects[ai], rects[aj]):
+                        bi.append((f, ai, aj))
+            for a in range(na):
+                for oi, o in enumerate(obs):
+                    if V.collision_circle_and_rect((o[0], o[1], o[2] if len(o) == 3 else V.OBS_RADIUS_VIS), rects[a]):
+                        bs.append((f, a, oi))
+        assert inter == bi and static == bs
+        if trial % 3 == 0:
+            assert bi and bs                                      # the crowded scenes do collide
