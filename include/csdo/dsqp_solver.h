@@ -29,6 +29,7 @@
 #include <cstdint>
 #include <cstring>
 #include <functional>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <tuple>
@@ -104,6 +105,31 @@ inline void check(int rc, csdo_handle *h, const char *what) {
   if (rc != CSDO_OK) throw std::runtime_error(std::string(what) + ": " + (h ? csdo_last_error(h) : "no handle"));
 }
 
+// A library handle (stream, scratch, work queue) is kept per (device, parameters) for the life of the process
+// instead of being created and destroyed by every call: a fresh handle costs ~4-10 ms (stream + first
+// allocations) next to ~16 ms for refining one 25-agent instance.  Calls that share a handle are serialised.
+class HandleLease {
+ public:
+  HandleLease(const csdo_params &P, int device) : lock_(mutex()) {
+    for (Entry &e : cache())
+      if (e.device == device && std::memcmp(&e.params, &P, sizeof(csdo_params)) == 0) { h_ = e.h; return; }
+    csdo_handle *h = nullptr;
+    check(csdo_create(&P, device, &h), nullptr, "csdo_create");
+    cache().push_back(Entry{device, P, h});
+    h_ = h;
+  }
+  csdo_handle *get() const { return h_; }
+
+ private:
+  struct Entry { int device; csdo_params params; csdo_handle *h; };
+  // (never destroyed: at static-destruction time the CUDA runtime may already be gone; the driver reclaims
+  // the stream and the allocations when the process ends)
+  static std::vector<Entry> &cache() { static std::vector<Entry> *v = new std::vector<Entry>(); return *v; }
+  static std::mutex &mutex() { static std::mutex m; return m; }
+  std::unique_lock<std::mutex> lock_;
+  csdo_handle *h_ = nullptr;
+};
+
 // one instance -> the flat batch layout of csdo_dsqp.h
 struct Packed {
   int32_t inst_agent_ptr[2] = {0, 0};
@@ -171,22 +197,19 @@ inline void unpack_planes(const csdo_detail::Packed &p, std::vector<std::vector<
 inline bool build(const std::vector<std::vector<OptimizeResult>> &x0_bar, const csdo_params &P, int device,
                   csdo_detail::Packed &p, std::vector<int32_t> *partner) {
   csdo_detail::pack_guess(x0_bar, p);
-  csdo_handle *h = nullptr;
-  csdo_detail::check(csdo_create(&P, device, &h), nullptr, "csdo_create");
+  csdo_detail::HandleLease lease(P, device);
+  csdo_handle *h = lease.get();
   const int Na = p.inst_agent_ptr[1];
   int32_t legal = 1;
   csdo_batch b = p.view();
-  try {
-    csdo_detail::check(csdo_planes_count(h, &b, p.plane_ptr.data(), &legal), h, "csdo_planes_count");
-    const int total = p.plane_ptr[Na];
-    p.plane_t.assign(total, 0);
-    p.plane_abc.assign((size_t)12 * total, 0.0);
-    if (partner) partner->assign(total, 0);
-    csdo_detail::check(csdo_planes_fill_partners(h, &b, p.plane_ptr.data(), p.plane_t.data(), p.plane_abc.data(),
-                                                 partner ? partner->data() : nullptr),
-                       h, "csdo_planes_fill");
-  } catch (...) { csdo_destroy(h); throw; }
-  csdo_destroy(h);
+  csdo_detail::check(csdo_planes_count(h, &b, p.plane_ptr.data(), &legal), h, "csdo_planes_count");
+  const int total = p.plane_ptr[Na];
+  p.plane_t.assign(total, 0);
+  p.plane_abc.assign((size_t)12 * total, 0.0);
+  if (partner) partner->assign(total, 0);
+  csdo_detail::check(csdo_planes_fill_partners(h, &b, p.plane_ptr.data(), p.plane_t.data(), p.plane_abc.data(),
+                                               partner ? partner->data() : nullptr),
+                     h, "csdo_planes_fill");
   return legal != 0;
 }
 }  // namespace detail
@@ -222,13 +245,13 @@ inline void calcEqualInterPlanes(const std::vector<std::vector<OptimizeResult>> 
     for (int e = 0; e < 3; ++e) flat[3 * q + e] = neighbor_pairs[q][e];
   p.plane_t.assign(2 * neighbor_pairs.size(), 0);
   p.plane_abc.assign((size_t)24 * neighbor_pairs.size(), 0.0);
-  csdo_handle *h = nullptr;
-  csdo_detail::check(csdo_create(&P, device, &h), nullptr, "csdo_create");
-  csdo_batch b = p.view();
-  const int rc = csdo_planes_from_pairs(h, &b, (int64_t)neighbor_pairs.size(), flat.data(), p.plane_ptr.data(),
-                                        p.plane_t.data(), p.plane_abc.data());
-  if (rc != CSDO_OK) { std::string e = csdo_last_error(h); csdo_destroy(h); throw std::runtime_error("csdo_planes_from_pairs: " + e); }
-  csdo_destroy(h);
+  {
+    csdo_detail::HandleLease lease(P, device);
+    csdo_batch b = p.view();
+    csdo_detail::check(csdo_planes_from_pairs(lease.get(), &b, (int64_t)neighbor_pairs.size(), flat.data(),
+                                              p.plane_ptr.data(), p.plane_t.data(), p.plane_abc.data()),
+                       lease.get(), "csdo_planes_from_pairs");
+  }
   detail::unpack_planes(p, inter_planes);
 }
 
@@ -295,14 +318,14 @@ class SolverDSQP {
     int32_t inst_status = 0, inst_legal = 1;
     csdo_result r{traj.data(), corr.data(), status.data(), sqp.data(), nqp.data(), admm.data(), nfac.data(),
                   obj.data(), &inst_status, &inst_legal};
-    csdo_handle *h = nullptr;
-    csdo_detail::check(csdo_create(&P, device, &h), nullptr, "csdo_create");
-    const auto t0 = std::chrono::steady_clock::now();
-    csdo_batch b = p.view();
-    const int rc = csdo_refine(h, &b, &r);
-    max_individual_opt_runtime = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    if (rc != CSDO_OK) { std::string e = csdo_last_error(h); csdo_destroy(h); throw std::runtime_error("csdo_refine: " + e); }
-    csdo_destroy(h);
+    {
+      csdo_detail::HandleLease lease(P, device);
+      const auto t0 = std::chrono::steady_clock::now();
+      csdo_batch b = p.view();
+      const int rc = csdo_refine(lease.get(), &b, &r);
+      max_individual_opt_runtime = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      csdo_detail::check(rc, lease.get(), "csdo_refine");
+    }
     solutions.assign(Na, {});
     corridors.assign(Na, {});
     num_iterations.assign(sqp.begin(), sqp.end());
